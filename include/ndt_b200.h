@@ -1,0 +1,146 @@
+/*
+ * ndt_b200.h -- C ABI of libndt_b200.so, the B200 drop-in for ndt's render path.
+ *
+ * The reference renders a frame with
+ *     render_image(scene*, name, depth_name, w, h, samples, stereo_mode, threads,
+ *                  aa_diff, aa_depth, max_optic_depth, img_copy, depth_copy)
+ * (ndt.c:900), called once per frame from main() (ndt.c:1933) after the kd-tree
+ * build (ndt.c:1899-1908) and camera_aim (ndt.c:1925).  Everything below that
+ * call -- the pthread row loop (ndt.c:803-849), render_pixel / get_pixel_color
+ * / get_ray_color / apply_lights (ndt.c:71-653), trace_kd and the kd traversal
+ * (object.c:683-747, kd-tree.c:482-625), the per-type intersect functions
+ * (objects/<type>.c) and pixel_d2c (image.h:36-39) -- is what this library
+ * replaces.  Everything above it (CLI, scene and object plugins, kd build,
+ * camera aim) keeps running unmodified on the host.
+ *
+ * Plain pointers and sizes only: no torch / CUDA types in any signature
+ * (stream handles travel as void*).  All functions return 0 on success or a
+ * negative ndt_b200_status; ndt_b200_last_error() gives the message for the
+ * calling thread.  The library never calls exit() (the reference's convention,
+ * object.c:233-236, is not acceptable for a library).  There is NO CPU
+ * fallback: without a usable CUDA device every device entry point fails with
+ * NDT_B200_E_CUDA.
+ */
+#ifndef NDT_B200_H
+#define NDT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#include "ndt_flat.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ndt_b200_status {
+    NDT_B200_OK = 0,
+    NDT_B200_E_ARG = -1,          /* bad argument / inconsistent scene */
+    NDT_B200_E_UNSUPPORTED = -2,  /* object type, light type or camera outside the device path */
+    NDT_B200_E_NOMEM = -3,
+    NDT_B200_E_CUDA = -4,         /* CUDA runtime failure (message has the cudaError string) */
+    NDT_B200_E_OVERFLOW = -5,     /* ray pool / traversal stack exhausted: render smaller tiles */
+    NDT_B200_E_STATE = -6         /* call order (e.g. render before upload) */
+} ndt_b200_status;
+
+typedef struct ndt_b200_ctx ndt_b200_ctx;
+
+/* Host services the flattener needs from the ndt host it is embedded in.
+ * object_get_bounds: object.c:582 (Nelder-Mead bounding sphere, bounding.c:177);
+ * the flattener calls it for every object whose lazily computed bounds have
+ * not been produced yet (object.c:608-615), so that both sides of a parity
+ * check use the very same centre/radius. */
+typedef struct ndt_b200_host_api {
+    int (*object_get_bounds)(void *object);
+} ndt_b200_host_api;
+
+/* What one render call did.  "rays" are nearest-hit queries, i.e. trace_kd
+ * calls (object.c:683): primary, reflection/refraction, shadow. */
+typedef struct ndt_b200_stats {
+    uint64_t rays_primary;
+    uint64_t rays_bounce;
+    uint64_t rays_shadow;
+    uint64_t rays_unique;     /* sum of the three */
+    uint64_t rays_ref;        /* what the reference executes for the same frame: every
+                                 pixel's ray tree times its sample-loop count (ndt.c:488) */
+    uint64_t samples;         /* sum over pixels of sample-loop iterations */
+    uint64_t flops;           /* algorithmic fp64 operations (counting build only, else 0) */
+    uint64_t launches;        /* kernels launched */
+    uint32_t generations;     /* bounce generations processed */
+    uint32_t reserved;
+    double device_ms;         /* CUDA-event time of the kernels of this call */
+} ndt_b200_stats;
+
+/* ---- host side: struct-ABI adapter ------------------------------------- */
+
+/* Replaces the entry of render_image (ndt.c:900-929): reads the host's scene
+ * and the global kd-tree (ndt.c:68) through the struct ABI in ndt_abi.h,
+ * forces all lazily prepared state (sphere.c:18-32, hcube.c:155-170,
+ * object.c:608-615), applies the dirX *= w/h scaling (ndt.c:926) to its own
+ * copy and emits the flat scene.  `scene` is a `scene*`, `kdtree` a
+ * `kd_tree_t*` of the reference.  Unknown object types, custom
+ * get_color/get_reflect hooks, area lights and VR/PANO cameras are refused
+ * with NDT_B200_E_UNSUPPORTED. */
+int ndt_b200_flatten(const void *scene, const void *kdtree, int width, int height,
+                     int max_optic_depth, int specular,
+                     const ndt_b200_host_api *host, ndt_flat_scene **out);
+void ndt_b200_free_flat(ndt_flat_scene *fs);
+/* structural check of a blob received from disk or another rank */
+int ndt_b200_flat_validate(const void *blob, size_t bytes);
+
+/* ---- device side --------------------------------------------------------- */
+
+int ndt_b200_init(int device, ndt_b200_ctx **ctx);
+void ndt_b200_destroy(ndt_b200_ctx *ctx);
+
+/* copy the flat scene to HBM (one cudaMemcpyAsync of the whole blob) */
+int ndt_b200_upload(ndt_b200_ctx *ctx, const ndt_flat_scene *fs);
+
+/* options: 0 = default */
+#define NDT_B200_OPT_COUNT_FLOPS 1u   /* run the instrumented kernels and fill stats.flops */
+int ndt_b200_set_options(ndt_b200_ctx *ctx, uint32_t options);
+
+/* Render the tile [x0,x0+tw) x [y0,y0+th) of the uploaded frame into HOST
+ * buffers laid out tile-row-major (tw*th elements): fp64 RGBA as render_line
+ * stores it (ndt.c:752, image.h:22-26), 8-bit RGBA through pixel_d2c
+ * (image.h:36-39), hit flag and object id of the primary ray (what
+ * get_ray_color tests at ndt.c:376) and 1/distance (ndt.c:363-373).  Any
+ * output pointer may be NULL.  Synchronous; device->host copies included. */
+int ndt_b200_render_tile(ndt_b200_ctx *ctx, int x0, int y0, int tw, int th,
+                         double *rgba_f64, uint8_t *rgba_u8, uint8_t *hit,
+                         int32_t *obj_id, double *inv_depth, ndt_b200_stats *stats);
+
+/* Same, but the outputs are DEVICE pointers and the work is only enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = the context's stream).  Statistics
+ * are available from ndt_b200_last_stats() after the stream is synchronised
+ * by ndt_b200_sync(). */
+int ndt_b200_launch_tile(ndt_b200_ctx *ctx, int x0, int y0, int tw, int th,
+                         void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
+                         void *d_obj_id, void *d_inv_depth);
+int ndt_b200_sync(ndt_b200_ctx *ctx);
+int ndt_b200_last_stats(ndt_b200_ctx *ctx, ndt_b200_stats *stats);
+/* the stream all of a context's work is enqueued on (cudaStream_t as void*) */
+void *ndt_b200_stream(ndt_b200_ctx *ctx);
+
+/* Drop-in for render_image (ndt.c:900), same parameters and return value
+ * (1).  `kdtree` is the extra argument: the reference reads its global
+ * (ndt.c:68), a library cannot.  Supports what the device path supports:
+ * samples == 1, stereo mode MONO, recursive_aa off; anything else returns a
+ * negative status instead of rendering.  When img_copy is non-NULL it
+ * receives the fp64 frame exactly like ndt.c:1024-1027. */
+int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_api *host,
+                          char *name, char *depth_name, int width, int height,
+                          int samples, int stereo_mode, int threads, int aa_diff,
+                          int aa_depth, int max_optic_depth, int specular,
+                          void *img_copy, void *depth_copy);
+
+/* one FP64 pipe probe: returns sustained GFLOP/s of an all-SM chain of
+ * dependent-free DFMA (fused=1) or DMUL+DADD pairs (fused=0); the roofline
+ * denominators of bench.py */
+int ndt_b200_fp64_peak(ndt_b200_ctx *ctx, int fused, double *gflops);
+
+const char *ndt_b200_last_error(void);
+const char *ndt_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDT_B200_H */
