@@ -1,0 +1,230 @@
+"""ndt_b200 -- B200-native render path for the N-dimensional tracer `ndt`.
+
+Host-side mirror of the C ABI in include/ndt_b200.h (ctypes; no compute
+happens in Python).  The product path is libndt_b200.so: hand-written CUDA
+for sm_100a behind plain-C entry points.  There is no CPU fallback -- every
+device call raises NdtB200Error when the library or a CUDA device is missing.
+
+    flat = ndt_b200.flatten(scene_ptr, kdtree_ptr, w, h, host_get_bounds=ptr)
+    with ndt_b200.Context(device=0) as ctx:
+        ctx.upload(flat)
+        frame = ctx.render_tile(0, 0, w, h)      # Frame: rgba_f64, rgba_u8, hit, obj_id, inv_depth, stats
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libndt_b200.so")
+
+OPT_COUNT_FLOPS = 1
+
+
+class NdtB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ndt_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_bounce", C.c_uint64),
+                ("rays_shadow", C.c_uint64), ("rays_unique", C.c_uint64),
+                ("rays_ref", C.c_uint64), ("samples", C.c_uint64),
+                ("flops", C.c_uint64), ("launches", C.c_uint64),
+                ("generations", C.c_uint32), ("reserved", C.c_uint32),
+                ("device_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class _HostApi(C.Structure):
+    _fields_ = [("object_get_bounds", C.c_void_p)]
+
+
+class FlatHeader(C.Structure):
+    """include/ndt_flat.h: ndt_flat_header"""
+    _fields_ = [("magic", C.c_uint32), ("version", C.c_uint32), ("total_bytes", C.c_uint64),
+                ("n", C.c_int32), ("npad", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("max_optic_depth", C.c_int32), ("specular", C.c_int32),
+                ("n_items", C.c_int32), ("n_objects", C.c_int32),
+                ("n_nodes", C.c_int32), ("n_leaf_refs", C.c_int32), ("n_inf", C.c_int32),
+                ("n_lights", C.c_int32), ("max_leaf", C.c_int32), ("tree_depth", C.c_int32),
+                ("use_focal", C.c_int32), ("reserved", C.c_int32),
+                ("bg", C.c_double * 4), ("ambient", C.c_double * 3), ("focal_scale", C.c_double),
+                ("off_camera", C.c_uint64), ("off_aabb", C.c_uint64), ("off_objects", C.c_uint64),
+                ("off_bspheres", C.c_uint64), ("off_geom", C.c_uint64), ("n_geom", C.c_uint64),
+                ("off_nodes", C.c_uint64), ("off_leaf_refs", C.c_uint64), ("off_inf", C.c_uint64),
+                ("off_lights", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libndt_b200.so (built in-tree by ndt_b200/csrc/Makefile).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NdtB200Error(-4, f"{LIB_PATH} not built: run `make -C ndt_b200/csrc` "
+                               "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.ndt_b200_last_error.restype = C.c_char_p
+    L.ndt_b200_version.restype = C.c_char_p
+    L.ndt_b200_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(_HostApi), C.POINTER(C.c_void_p)]
+    L.ndt_b200_free_flat.argtypes = [C.c_void_p]
+    L.ndt_b200_free_flat.restype = None
+    L.ndt_b200_flat_validate.argtypes = [C.c_void_p, C.c_size_t]
+    L.ndt_b200_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.ndt_b200_destroy.argtypes = [C.c_void_p]
+    L.ndt_b200_destroy.restype = None
+    L.ndt_b200_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndt_b200_set_options.argtypes = [C.c_void_p, C.c_uint32]
+    L.ndt_b200_render_tile.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5 + [C.POINTER(Stats)]
+    L.ndt_b200_launch_tile.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5
+    L.ndt_b200_sync.argtypes = [C.c_void_p]
+    L.ndt_b200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.ndt_b200_stream.argtypes = [C.c_void_p]
+    L.ndt_b200_stream.restype = C.c_void_p
+    L.ndt_b200_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.ndt_b200_render_image.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_HostApi), C.c_char_p, C.c_char_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise NdtB200Error(rc, lib().ndt_b200_last_error().decode(errors="replace"))
+    return rc
+
+
+class FlatScene:
+    """A flat scene blob (include/ndt_flat.h) held as bytes in host memory."""
+
+    def __init__(self, blob):
+        self.blob = bytes(blob)
+        self.header = FlatHeader.from_buffer_copy(self.blob[:C.sizeof(FlatHeader)])
+        _check(lib().ndt_b200_flat_validate(self.blob, len(self.blob)))
+
+    @classmethod
+    def load(cls, path):
+        import gzip
+        op = gzip.open if str(path).endswith(".gz") else open
+        with op(path, "rb") as f:
+            return cls(f.read())
+
+    def save(self, path):
+        import gzip
+        op = gzip.open if str(path).endswith(".gz") else open
+        with op(path, "wb") as f:
+            f.write(self.blob)
+
+    def retarget(self, width, height):
+        """The same scene for another frame size is NOT a header edit: the camera
+        basis was scaled for width/height (ndt.c:926).  Only equal aspect ratios
+        can be retargeted without re-flattening."""
+        h = self.header
+        if width * h.height != height * h.width:
+            raise ValueError("aspect ratio differs; flatten the host scene again")
+        hdr = FlatHeader.from_buffer_copy(self.blob[:C.sizeof(FlatHeader)])
+        hdr.width, hdr.height = width, height
+        return FlatScene(bytes(hdr) + self.blob[C.sizeof(FlatHeader):])
+
+    def __len__(self):
+        return len(self.blob)
+
+
+def flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth=128, specular=1, host_get_bounds=None):
+    """ndt_b200_flatten: host `scene*` + `kd_tree_t*` (ndt.c:68) -> FlatScene."""
+    L = lib()
+    host = _HostApi(host_get_bounds)
+    out = C.c_void_p()
+    _check(L.ndt_b200_flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth, specular,
+                              C.byref(host), C.byref(out)))
+    try:
+        total = C.c_uint64.from_address(out.value + 8).value
+        return FlatScene(C.string_at(out.value, total))
+    finally:
+        L.ndt_b200_free_flat(out)
+
+
+class Frame:
+    def __init__(self, tw, th, want):
+        self.rgba_f64 = np.empty((th, tw, 4), np.float64) if "f64" in want else None
+        self.rgba_u8 = np.empty((th, tw, 4), np.uint8) if "u8" in want else None
+        self.hit = np.empty((th, tw), np.uint8) if "hit" in want else None
+        self.obj_id = np.empty((th, tw), np.int32) if "id" in want else None
+        self.inv_depth = np.empty((th, tw), np.float64) if "depth" in want else None
+        self.stats = None
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Context:
+    """One per GPU (ndt_b200_ctx).  Not re-entrant."""
+
+    ALL = ("f64", "u8", "hit", "id", "depth")
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().ndt_b200_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().ndt_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self, options):
+        _check(lib().ndt_b200_set_options(self._h, options))
+
+    def upload(self, flat):
+        self._flat = flat  # keep the bytes alive until the async copy is consumed
+        _check(lib().ndt_b200_upload(self._h, flat.blob))
+
+    def render_tile(self, x0, y0, tw, th, want=ALL, out=None):
+        """ndt_b200_render_tile: host buffers, device->host copies included."""
+        fr = out or Frame(tw, th, want)
+        st = Stats()
+        _check(lib().ndt_b200_render_tile(self._h, x0, y0, tw, th, _p(fr.rgba_f64), _p(fr.rgba_u8),
+                                          _p(fr.hit), _p(fr.obj_id), _p(fr.inv_depth), C.byref(st)))
+        fr.stats = st
+        return fr
+
+    def launch_tile(self, x0, y0, tw, th, d_f64=None, d_u8=None, d_hit=None, d_id=None, d_depth=None):
+        """ndt_b200_launch_tile: outputs are DEVICE pointers (ints, e.g. tensor.data_ptr())."""
+        _check(lib().ndt_b200_launch_tile(self._h, x0, y0, tw, th, d_f64, d_u8, d_hit, d_id, d_depth))
+
+    def sync(self):
+        _check(lib().ndt_b200_sync(self._h))
+        st = Stats()
+        _check(lib().ndt_b200_last_stats(self._h, C.byref(st)))
+        return st
+
+    @property
+    def stream(self):
+        return lib().ndt_b200_stream(self._h)
+
+    def fp64_peak(self, fused):
+        g = C.c_double(0)
+        _check(lib().ndt_b200_fp64_peak(self._h, 1 if fused else 0, C.byref(g)))
+        return g.value

@@ -1,0 +1,691 @@
+/*
+ * kernels.cu -- wavefront kernels and the device half of the C ABI (ndt_b200.h).
+ *
+ * One render = a loop over bounce generations:
+ *   k_generation<NP>   persistent CTAs; every warp pulls 32 rays at a time from
+ *                      the generation's queue (one atomicAdd per warp), traces
+ *                      them (wave.cuh: nearest hit + lighting + shadow rays),
+ *                      writes one RayRec per ray and appends the reflection /
+ *                      refraction rays it spawned to the next generation's
+ *                      queue; slots are handed out per warp with two ballots
+ *                      and one atomicAdd.
+ *   k_resolve          folds generation g+1 into g (deepest first), replaying
+ *                      the reference's colour arithmetic in its own order.
+ *   k_finish<>         generation 0 -> pixels: sample-loop replay (ndt.c:488),
+ *                      fp64 RGBA as 2x16-byte stores, u8 RGBA as one 4-byte
+ *                      store per pixel (pixel_d2c, image.h:36-39), statistics.
+ *
+ * Generation 0 maps a warp to an 8x4 pixel block so that the 32 primary rays
+ * of a warp walk the same kd leaves.  fp64 arithmetic is never contracted
+ * (-fmad=false) -- see core.cuh.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "ndt_abi.h"
+#include "ndt_internal.h"
+#include "wave.cuh"
+
+using namespace ndt;
+
+#define BLOCK 128
+
+struct GenArgs {
+    int gen;                 /* 0: rays are generated from pixels */
+    int start, count;        /* this generation's slots are [start, start+count) */
+    int n0;                  /* slots of generation 0 (tile padded to 8x4 blocks) */
+    int cap;                 /* record pool capacity */
+    int x0, y0, tw, th, bpr; /* tile, and 8-pixel blocks per tile row */
+    RayRec *rec;
+    void *rays;              /* RayIn<NP>[cap - n0], slot s lives at rays[s - n0] */
+    int *tail;               /* next free slot */
+    int *next;               /* work counter of this launch */
+    int *overflow;           /* [0] ray pool, [1] kd stack */
+    unsigned long long *stats; /* [0] shadow rays [1] flops [2] rays_ref [3] samples [4] hit pixels */
+    uint8_t *out_hit;
+    int32_t *out_id;
+    double *out_depth;
+    uint32_t *mb_bits;
+    uint32_t mb_stride, mb_words, mb_shift;
+};
+
+template <int NP, bool CNT>
+__global__ void __launch_bounds__(BLOCK) k_generation(const Scene sc, const GenArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    Mailbox mb;
+    mb.bits = a.mb_bits; mb.stride = a.mb_stride;
+    mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
+    mb.words = a.mb_words; mb.group_shift = a.mb_shift;
+    mb.dirty = ~0ull;            /* first clear() wipes the whole column */
+    Tally<CNT> tally;
+    unsigned long long shadow_total = 0;
+    int kd_overflow = 0;
+    RayIn<NP> *rays = (RayIn<NP> *)a.rays;
+
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.next, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.count) break;
+        const int r = base + lane;
+        bool active = r < a.count;
+        double o[NP], v[NP], frac = 1.0;
+        int depth = sc.max_optic_depth;
+        int tx = 0, ty = 0;
+        if (a.gen == 0) {
+            const int blk = r >> 5;
+            tx = (blk % a.bpr) * 8 + (lane & 7);
+            ty = (blk / a.bpr) * 4 + (lane >> 3);
+            active = active && tx < a.tw && ty < a.th;
+            if (active) primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
+        } else if (active) {
+            const RayIn<NP> *in = rays + (a.start + r - a.n0);
+            NDT_UNROLL
+            for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
+            frac = in->frac;
+            depth = in->depth;
+        }
+
+        RayRec rec;
+        Spawn<NP> sp;
+        sp.want_refl = sp.want_refr = 0;
+        int p_hit = 0, p_id = -1;
+        double p_dist = -1.0;
+        uint32_t nsh = 0;
+        if (active) {
+            process_ray<NP, CNT>(sc, mb, o, v, frac, depth, rec, sp, p_hit, p_id, p_dist, nsh, kd_overflow, tally);
+            rec.nrays = 1u + nsh;
+            shadow_total += nsh;
+        }
+
+        /* hand out slots of the next generation: two ballots, one atomic per warp */
+        const bool q1 = active && sp.want_refl == 1;
+        const bool q2 = active && sp.want_refr == 1;
+        const unsigned b1 = __ballot_sync(0xffffffffu, q1);
+        const unsigned b2 = __ballot_sync(0xffffffffu, q2);
+        const int total = __popc(b1) + __popc(b2);
+        int wbase = 0;
+        if (total > 0) {
+            if (lane == 0) wbase = atomicAdd(a.tail, total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        }
+        const bool fits = wbase + total <= a.cap;
+        if (total > 0 && !fits && lane == 0) atomicExch(a.overflow, 1);
+        const unsigned lt = (1u << lane) - 1u;
+        if (active) {
+            if (sp.want_refl == 2) rec.child_refl = CHILD_BLACK;
+            if (sp.want_refr == 2) rec.child_refr = CHILD_BLACK;
+            if (q1) {
+                const int s = wbase + __popc(b1 & lt);
+                rec.child_refl = fits ? s : CHILD_BLACK;
+                if (fits) {
+                    RayIn<NP> *out = rays + (s - a.n0);
+                    NDT_UNROLL
+                    for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refl_dir[i]; }
+                    out->frac = sp.refl_frac; out->depth = depth - 1; out->pad = 0;
+                }
+            }
+            if (q2) {
+                const int s = wbase + __popc(b1) + __popc(b2 & lt);
+                rec.child_refr = fits ? s : CHILD_BLACK;
+                if (fits) {
+                    RayIn<NP> *out = rays + (s - a.n0);
+                    NDT_UNROLL
+                    for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refr_dir[i]; }
+                    out->frac = sp.refr_frac; out->depth = depth - 1; out->pad = 0;
+                }
+            }
+            a.rec[a.start + r] = rec;
+            if (a.gen == 0) {
+                const size_t p = (size_t)ty * a.tw + tx;
+                if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
+                if (a.out_id) a.out_id[p] = p_id;
+                if (a.out_depth) a.out_depth[p] = (p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
+            }
+        } else if (a.gen == 0 && r < a.count) {
+            /* padding lane of a partial 8x4 block: keep the record defined */
+            RayRec z;
+            z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
+            z.h[0] = z.h[1] = z.h[2] = 0.0;
+            z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = 0;
+            a.rec[a.start + r] = z;
+        }
+    }
+
+    /* statistics: one atomic per warp */
+    for (int d = 16; d > 0; d >>= 1) shadow_total += __shfl_down_sync(0xffffffffu, shadow_total, d);
+    if (lane == 0 && shadow_total) atomicAdd(&a.stats[0], shadow_total);
+    if (CNT) {
+        unsigned long long f = tally.f;
+        for (int d = 16; d > 0; d >>= 1) f += __shfl_down_sync(0xffffffffu, f, d);
+        if (lane == 0 && f) atomicAdd(&a.stats[1], f);
+    }
+    if (kd_overflow) atomicExch(a.overflow + 1, 1);
+}
+
+__global__ void k_resolve(RayRec *rec, int start, int count, int specular)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    RayRec r = rec[start + i];
+    if (r.child_refl == CHILD_NONE && r.child_refr == CHILD_NONE) return;
+    const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
+    const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
+    resolve_rec(r, c1, c2, specular);
+    rec[start + i] = r;
+}
+
+/* generation 0 -> pixels */
+__global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
+                         double *out_f64, uint8_t *out_u8, unsigned long long *stats)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long rays_ref = 0, samples = 0, hits = 0;
+    if (p < tw * th) {
+        const int tx = p % tw, ty = p / tw;
+        const int slot = ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7);
+        RayRec r = rec[slot];
+        const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
+        const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
+        resolve_rec(r, c1, c2, specular);
+        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4];
+        const int ns = replay_samples(l, o);
+        if (out_f64) {
+            double2 *d = reinterpret_cast<double2 *>(out_f64 + 4 * (size_t)p);
+            d[0] = make_double2(o[0], o[1]);
+            d[1] = make_double2(o[2], o[3]);
+        }
+        if (out_u8) {
+            uchar4 c = make_uchar4(d2c(o[0]), d2c(o[1]), d2c(o[2]), d2c(o[3]));
+            reinterpret_cast<uchar4 *>(out_u8)[p] = c;
+        }
+        rays_ref = (unsigned long long)r.nrays * (unsigned long long)ns;
+        samples = (unsigned long long)ns;
+        hits = r.flags & 1u;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        rays_ref += __shfl_down_sync(0xffffffffu, rays_ref, d);
+        samples += __shfl_down_sync(0xffffffffu, samples, d);
+        hits += __shfl_down_sync(0xffffffffu, hits, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (rays_ref) atomicAdd(&stats[2], rays_ref);
+        if (samples) atomicAdd(&stats[3], samples);
+        if (hits) atomicAdd(&stats[4], hits);
+    }
+}
+
+/* FP64 pipe probe: 8 independent chains per thread */
+template <bool FUSED> __global__ void k_fp64_probe(double *sink, int iters)
+{
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        if (FUSED) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        } else {
+            a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c);
+            a2 = __dadd_rn(__dmul_rn(a2, m), c); a3 = __dadd_rn(__dmul_rn(a3, m), c);
+            a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+            a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) sink[0] = s;
+}
+
+/* ---------------------------------------------------------------------------
+ * host runtime
+ * ------------------------------------------------------------------------- */
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return ndt_set_error(NDT_B200_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+struct ndt_b200_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    /* scene */
+    char *d_blob; size_t blob_cap;
+    ndt_flat_header hdr;
+    Scene sc;
+    int have_scene;
+    /* pools */
+    RayRec *d_rec; size_t rec_cap;       /* records */
+    void *d_rays; size_t rays_bytes;
+    uint32_t *d_mb; size_t mb_bytes;
+    int *d_ctr;                          /* [0] tail [1] next [2..3] overflow */
+    unsigned long long *d_stats;         /* 8 counters */
+    int *h_ctr; unsigned long long *h_stats; /* pinned mirrors */
+    /* outputs for the host-buffer entry point */
+    char *d_out; size_t out_cap;
+    double bounce_factor;
+    uint32_t options;
+    ndt_b200_stats last;
+    int grid_blocks[2][8];               /* cached occupancy per (CNT, NP/2) */
+};
+
+template <int NP, bool CNT> static int blocks_per_sm()
+{
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generation<NP, CNT>, BLOCK, 0) != cudaSuccess || b < 1) b = 1;
+    return b;
+}
+
+template <int NP, bool CNT>
+static void launch_generation(int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
+{
+    k_generation<NP, CNT><<<blocks, BLOCK, 0, st>>>(sc, a);
+}
+
+static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
+{
+    int &g = c->grid_blocks[cnt ? 1 : 0][np / 2];
+    if (g == 0) {
+        int b = 1;
+        switch (np) {
+        case 4:  b = cnt ? blocks_per_sm<4, true>()  : blocks_per_sm<4, false>();  break;
+        case 6:  b = cnt ? blocks_per_sm<6, true>()  : blocks_per_sm<6, false>();  break;
+        case 8:  b = cnt ? blocks_per_sm<8, true>()  : blocks_per_sm<8, false>();  break;
+        case 10: b = cnt ? blocks_per_sm<10, true>() : blocks_per_sm<10, false>(); break;
+        case 12: b = cnt ? blocks_per_sm<12, true>() : blocks_per_sm<12, false>(); break;
+        }
+        g = b * c->sm_count;
+    }
+    return g;
+}
+
+static void dispatch_generation(int np, bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
+{
+#define GO(N) do { if (cnt) launch_generation<N, true>(blocks, st, sc, a); else launch_generation<N, false>(blocks, st, sc, a); } while (0)
+    switch (np) {
+    case 4: GO(4); break;
+    case 6: GO(6); break;
+    case 8: GO(8); break;
+    case 10: GO(10); break;
+    case 12: GO(12); break;
+    }
+#undef GO
+}
+
+static size_t rayin_bytes(int np) { return (size_t)(2 * np + 2) * sizeof(double); }
+
+extern "C" int ndt_b200_init(int device, ndt_b200_ctx **out)
+{
+    if (!out) return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_init: NULL ctx pointer");
+    *out = NULL;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ndt_set_error(NDT_B200_E_CUDA, "no CUDA device (%s); libndt_b200 has no CPU path",
+                             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return ndt_set_error(NDT_B200_E_ARG, "device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    ndt_b200_ctx *c = (ndt_b200_ctx *)calloc(1, sizeof *c);
+    if (!c) return ndt_set_error(NDT_B200_E_NOMEM, "out of memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc(&c->d_ctr, 8 * sizeof(int)));
+    CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&c->h_ctr, 8 * sizeof(int)));
+    CK(cudaMallocHost(&c->h_stats, 8 * sizeof(unsigned long long)));
+    c->bounce_factor = 6.0;
+    *out = c;
+    return 0;
+}
+
+extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_blob); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
+    cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out);
+    cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+extern "C" void *ndt_b200_stream(ndt_b200_ctx *c) { return c ? (void *)c->stream : NULL; }
+
+extern "C" int ndt_b200_set_options(ndt_b200_ctx *c, uint32_t options)
+{
+    if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    c->options = options;
+    return 0;
+}
+
+extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
+{
+    if (!c || !fs) return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_upload: NULL argument");
+    const ndt_flat_header *h = &fs->h;
+    int r = ndt_b200_flat_validate(fs, (size_t)h->total_bytes);
+    if (r) return r;
+    if (h->npad < 4 || h->npad > 12)
+        return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d dimensions: kernels are instantiated for 3..12", h->n);
+    CK(cudaSetDevice(c->device));
+    if (c->blob_cap < h->total_bytes) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_blob);
+        c->d_blob = NULL; c->blob_cap = 0;
+        size_t cap = (size_t)h->total_bytes + (size_t)h->total_bytes / 4 + 4096;
+        CK(cudaMalloc(&c->d_blob, cap));
+        c->blob_cap = cap;
+    }
+    CK(cudaMemcpyAsync(c->d_blob, fs, (size_t)h->total_bytes, cudaMemcpyHostToDevice, c->stream));
+    c->hdr = *h;
+    Scene &s = c->sc;
+    char *b = c->d_blob;
+    s.cam = (const double *)(b + h->off_camera);
+    s.aabb = (const double *)(b + h->off_aabb);
+    s.bs = (const double *)(b + h->off_bspheres);
+    s.geom = (const double *)(b + h->off_geom);
+    s.obj = (const ndt_flat_object *)(b + h->off_objects);
+    s.nodes = (const ndt_flat_node *)(b + h->off_nodes);
+    s.leaf = (const int32_t *)(b + h->off_leaf_refs);
+    s.inf = (const int32_t *)(b + h->off_inf);
+    s.lights = (const ndt_flat_light *)(b + h->off_lights);
+    s.n = h->n; s.n_items = h->n_items; s.n_objects = h->n_objects; s.n_nodes = h->n_nodes;
+    s.n_inf = h->n_inf; s.n_lights = h->n_lights;
+    s.max_optic_depth = h->max_optic_depth; s.specular = h->specular; s.use_focal = h->use_focal;
+    s.width = h->width; s.height = h->height;
+    for (int k = 0; k < 4; ++k) s.bg[k] = h->bg[k];
+    for (int k = 0; k < 3; ++k) s.ambient[k] = h->ambient[k];
+    s.focal_scale = h->focal_scale;
+    if (h->tree_depth + 2 > KD_STACK)
+        return ndt_set_error(NDT_B200_E_UNSUPPORTED, "kd-tree depth %d exceeds the traversal stack (%d)", h->tree_depth, KD_STACK);
+    c->have_scene = 1;
+    return 0;
+}
+
+static int ensure_pools(ndt_b200_ctx *c, int n0, int np, int grid_threads)
+{
+    size_t want = (size_t)n0 + (size_t)((double)n0 * c->bounce_factor) + 65536;
+    if (want > 0x7ffffff0u) want = 0x7ffffff0u;
+    if (c->rec_cap < want) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_rec); c->d_rec = NULL; c->rec_cap = 0;
+        CK(cudaMalloc(&c->d_rec, want * sizeof(RayRec)));
+        c->rec_cap = want;
+    }
+    size_t rb = (c->rec_cap - (size_t)n0 + 1) * rayin_bytes(np);
+    if (c->rays_bytes < rb) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_rays); c->d_rays = NULL; c->rays_bytes = 0;
+        CK(cudaMalloc(&c->d_rays, rb));
+        c->rays_bytes = rb;
+    }
+    size_t words = ((size_t)c->hdr.n_items + 31) / 32;
+    if (words == 0) words = 1;
+    size_t mb = words * (size_t)grid_threads * sizeof(uint32_t);
+    if (c->mb_bytes < mb) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_mb); c->d_mb = NULL; c->mb_bytes = 0;
+        CK(cudaMalloc(&c->d_mb, mb));
+        c->mb_bytes = mb;
+    }
+    return 0;
+}
+
+extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
+                                    void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
+                                    void *d_obj_id, void *d_inv_depth)
+{
+    if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    if (!c->have_scene) return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_launch_tile before ndt_b200_upload");
+    const ndt_flat_header &h = c->hdr;
+    if (tw <= 0 || th <= 0 || x0 < 0 || y0 < 0 || x0 + tw > h.width || y0 + th > h.height)
+        return ndt_set_error(NDT_B200_E_ARG, "tile %dx%d+%d+%d outside the %dx%d frame", tw, th, x0, y0, h.width, h.height);
+    CK(cudaSetDevice(c->device));
+    const int np = h.npad;
+    const bool cnt = (c->options & NDT_B200_OPT_COUNT_FLOPS) != 0;
+    const int bpr = (tw + 7) / 8, bprows = (th + 3) / 4;
+    const long long n0ll = (long long)bpr * bprows * 32;
+    if (n0ll > 0x3fffffff) return ndt_set_error(NDT_B200_E_ARG, "tile too large; render in smaller tiles");
+    const int n0 = (int)n0ll;
+    const int full_grid = grid_for(c, np, cnt);
+    int r = ensure_pools(c, n0, np, full_grid * BLOCK);
+    if (r) return r;
+
+    GenArgs a;
+    memset(&a, 0, sizeof a);
+    a.n0 = n0; a.cap = (int)c->rec_cap;
+    a.x0 = x0; a.y0 = y0; a.tw = tw; a.th = th; a.bpr = bpr;
+    a.rec = c->d_rec; a.rays = c->d_rays;
+    a.tail = c->d_ctr; a.next = c->d_ctr + 1; a.overflow = c->d_ctr + 2;
+    a.stats = c->d_stats;
+    a.out_hit = (uint8_t *)d_hit; a.out_id = (int32_t *)d_obj_id; a.out_depth = (double *)d_inv_depth;
+    a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
+    a.mb_words = (uint32_t)((h.n_items + 31) / 32); if (a.mb_words == 0) a.mb_words = 1;
+    a.mb_shift = 0; while ((a.mb_words >> a.mb_shift) >= 64) ++a.mb_shift;
+
+    cudaStream_t st = c->stream;
+    c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0;
+    CK(cudaMemcpyAsync(c->d_ctr, c->h_ctr, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
+    CK(cudaEventRecord(c->ev0, st));
+
+    /* generation starts, for the backward fold */
+    int gstart[1024], gcount[1024], ngen = 0;
+    int start = 0, count = n0;
+    uint64_t launches = 0;
+    while (count > 0) {
+        if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
+        gstart[ngen] = start; gcount[ngen] = count;
+        a.gen = ngen; a.start = start; a.count = count;
+        if (ngen > 0) CK(cudaMemsetAsync(c->d_ctr + 1, 0, sizeof(int), st));
+        int blocks = (count + BLOCK - 1) / BLOCK;
+        if (blocks > full_grid) blocks = full_grid;
+        dispatch_generation(np, cnt, blocks, st, c->sc, a);
+        CK(cudaGetLastError());
+        ++launches; ++ngen;
+        CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (c->h_ctr[3]) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
+        if (c->h_ctr[2]) return ndt_set_error(NDT_B200_E_OVERFLOW, "ray pool exhausted (%zu records); render a smaller tile", c->rec_cap);
+        int tail = c->h_ctr[0];
+        start += count;
+        count = tail - start;
+    }
+    for (int g = ngen - 1; g >= 1; --g) {
+        k_resolve<<<(gcount[g] + 255) / 256, 256, 0, st>>>(c->d_rec, gstart[g], gcount[g], h.specular);
+        ++launches;
+    }
+    k_finish<<<(tw * th + 255) / 256, 256, 0, st>>>(c->d_rec, tw, th, bpr, h.specular,
+                                                   (double *)d_rgba_f64, (uint8_t *)d_rgba_u8, c->d_stats);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaMemcpyAsync(c->h_stats, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+
+    memset(&c->last, 0, sizeof c->last);
+    c->last.rays_primary = (uint64_t)tw * th;
+    c->last.rays_bounce = (uint64_t)(start - n0);
+    c->last.generations = (uint32_t)ngen;
+    c->last.launches = launches;
+    return 0;
+}
+
+extern "C" int ndt_b200_sync(ndt_b200_ctx *c)
+{
+    if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last.device_ms = ms;
+    c->last.rays_shadow = c->h_stats[0];
+    c->last.flops = c->h_stats[1];
+    c->last.rays_ref = c->h_stats[2];
+    c->last.samples = c->h_stats[3];
+    c->last.rays_unique = c->last.rays_primary + c->last.rays_bounce + c->last.rays_shadow;
+    return 0;
+}
+
+extern "C" int ndt_b200_last_stats(ndt_b200_ctx *c, ndt_b200_stats *s)
+{
+    if (!c || !s) return ndt_set_error(NDT_B200_E_ARG, "NULL argument");
+    *s = c->last;
+    return 0;
+}
+
+static void stats_add(ndt_b200_stats *acc, const ndt_b200_stats *s)
+{
+    acc->rays_primary += s->rays_primary; acc->rays_bounce += s->rays_bounce;
+    acc->rays_shadow += s->rays_shadow; acc->rays_unique += s->rays_unique;
+    acc->rays_ref += s->rays_ref; acc->samples += s->samples; acc->flops += s->flops;
+    acc->launches += s->launches;
+    if (s->generations > acc->generations) acc->generations = s->generations;
+    acc->device_ms += s->device_ms;
+}
+
+static int render_rows(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
+                       double *f64, uint8_t *u8, uint8_t *hit, int32_t *id, double *dep,
+                       ndt_b200_stats *acc, int depth)
+{
+    const size_t px = (size_t)tw * th;
+    const size_t need = px * (32 + 4 + 1 + 4 + 8) + 256;
+    if (c->out_cap < need) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_out); c->d_out = NULL; c->out_cap = 0;
+        CK(cudaMalloc(&c->d_out, need));
+        c->out_cap = need;
+    }
+    char *b = c->d_out;
+    double *d_f64 = (double *)b;              b += px * 32;
+    double *d_dep = (double *)b;              b += px * 8;
+    int32_t *d_id = (int32_t *)b;             b += px * 4;
+    uint8_t *d_u8 = (uint8_t *)b;             b += px * 4;
+    uint8_t *d_hit = (uint8_t *)b;
+    int r = ndt_b200_launch_tile(c, x0, y0, tw, th, f64 ? d_f64 : NULL, u8 ? d_u8 : NULL,
+                                 hit ? d_hit : NULL, id ? d_id : NULL, dep ? d_dep : NULL);
+    if (r == NDT_B200_E_OVERFLOW && depth < 12) {
+        cudaStreamSynchronize(c->stream);
+        if (th >= 2) {       /* rows are contiguous in a tile-row-major buffer: split along y */
+            int h1 = th / 2;
+            size_t o1 = (size_t)tw * h1;
+            r = render_rows(c, x0, y0, tw, h1, f64, u8, hit, id, dep, acc, depth + 1);
+            if (r) return r;
+            return render_rows(c, x0, y0 + h1, tw, th - h1, f64 ? f64 + 4 * o1 : NULL, u8 ? u8 + 4 * o1 : NULL,
+                               hit ? hit + o1 : NULL, id ? id + o1 : NULL, dep ? dep + o1 : NULL, acc, depth + 1);
+        }
+        c->bounce_factor *= 4.0;
+        return render_rows(c, x0, y0, tw, th, f64, u8, hit, id, dep, acc, depth + 1);
+    }
+    if (r) return r;
+    cudaStream_t st = c->stream;
+    if (f64) CK(cudaMemcpyAsync(f64, d_f64, px * 32, cudaMemcpyDeviceToHost, st));
+    if (u8)  CK(cudaMemcpyAsync(u8, d_u8, px * 4, cudaMemcpyDeviceToHost, st));
+    if (hit) CK(cudaMemcpyAsync(hit, d_hit, px, cudaMemcpyDeviceToHost, st));
+    if (id)  CK(cudaMemcpyAsync(id, d_id, px * 4, cudaMemcpyDeviceToHost, st));
+    if (dep) CK(cudaMemcpyAsync(dep, d_dep, px * 8, cudaMemcpyDeviceToHost, st));
+    r = ndt_b200_sync(c);
+    if (r) return r;
+    stats_add(acc, &c->last);
+    return 0;
+}
+
+extern "C" int ndt_b200_render_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
+                                    double *rgba_f64, uint8_t *rgba_u8, uint8_t *hit,
+                                    int32_t *obj_id, double *inv_depth, ndt_b200_stats *stats)
+{
+    if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    ndt_b200_stats acc;
+    memset(&acc, 0, sizeof acc);
+    int r = render_rows(c, x0, y0, tw, th, rgba_f64, rgba_u8, hit, obj_id, inv_depth, &acc, 0);
+    if (r) return r;
+    c->last = acc;
+    if (stats) *stats = acc;
+    return 0;
+}
+
+extern "C" int ndt_b200_fp64_peak(ndt_b200_ctx *c, int fused, double *gflops)
+{
+    if (!c || !gflops) return ndt_set_error(NDT_B200_E_ARG, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    double *sink = NULL;
+    CK(cudaMalloc(&sink, 64));
+    const int iters = 1 << 16, blocks = c->sm_count * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        if (fused) k_fp64_probe<true><<<blocks, threads, 0, c->stream>>>(sink, iters);
+        else k_fp64_probe<false><<<blocks, threads, 0, c->stream>>>(sink, iters);
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(sink);
+    /* per iteration and thread: 8 chains x 2 flops (mul+add, fused or not) */
+    double flops = (double)blocks * threads * (double)iters * 16.0;
+    *gflops = flops / (best * 1e-3) / 1e9;
+    return 0;
+}
+
+/* drop-in for render_image (ndt.c:900) */
+extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_api *host,
+                                     char *name, char *depth_name, int width, int height,
+                                     int samples, int stereo_mode, int threads, int aa_diff,
+                                     int aa_depth, int max_optic_depth, int specular,
+                                     void *img_copy, void *depth_copy)
+{
+    (void)threads; (void)aa_diff; (void)aa_depth; (void)name; (void)depth_name;
+    if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
+    if (stereo_mode != 0) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "stereo mode %d: only MONO (ndt.c:46) is on the device path", stereo_mode);
+    static ndt_b200_ctx *ctx = NULL;     /* one context per process, like the reference's global kdtree */
+    int r;
+    if (!ctx && (r = ndt_b200_init(0, &ctx))) return r;
+    ndt_flat_scene *fs = NULL;
+    if ((r = ndt_b200_flatten(scene, kdtree, width, height, max_optic_depth, specular, host, &fs))) return r;
+    /* render_image rescales the camera in place (ndt.c:925-926); callers rely on it */
+    {
+        ndtabi_scene *scn = (ndtabi_scene *)scene;
+        const double s = width / (double)height;
+        const int n = scn->cam.dirX.n, k = (n + 1) / 2;
+        for (int i = 0; i < 2 * k; ++i) scn->cam.dirX.v[i] = scn->cam.dirX.v[i] * s;
+    }
+    r = ndt_b200_upload(ctx, fs);
+    ndt_b200_free_flat(fs);
+    if (r) return r;
+    ndtabi_image *img = (ndtabi_image *)img_copy, *dimg = (ndtabi_image *)depth_copy;
+    double *f64 = NULL, *dep = NULL, *dep_rgba = NULL;
+    const size_t px = (size_t)width * height;
+    f64 = (double *)calloc(px, 32);
+    if (dimg) dep = (double *)calloc(px, 8);
+    if (!f64 || (dimg && !dep)) { free(f64); free(dep); return ndt_set_error(NDT_B200_E_NOMEM, "out of memory"); }
+    r = ndt_b200_render_tile(ctx, 0, 0, width, height, f64, NULL, NULL, NULL, dep, NULL);
+    if (r) { free(f64); free(dep); return r; }
+    if (img) {      /* image_copy (ndt.c:1024-1027): fp64 RGBA, row-major */
+        free(img->pixels);
+        memset(img, 0, sizeof *img);
+        img->width = width; img->height = height; img->pixel_width = 32;
+        img->allocated = (int)(px * 32);
+        img->pixels = (unsigned char *)f64;
+        f64 = NULL;
+    }
+    if (dimg) {     /* depth map: r=g=b=1/dist, a=1 (ndt.c:754-756) */
+        dep_rgba = (double *)calloc(px, 32);
+        if (dep_rgba) {
+            for (size_t i = 0; i < px; ++i) { dep_rgba[4 * i] = dep_rgba[4 * i + 1] = dep_rgba[4 * i + 2] = dep[i]; dep_rgba[4 * i + 3] = 1.0; }
+            free(dimg->pixels);
+            memset(dimg, 0, sizeof *dimg);
+            dimg->width = width; dimg->height = height; dimg->pixel_width = 32;
+            dimg->allocated = (int)(px * 32);
+            dimg->pixels = (unsigned char *)dep_rgba;
+        }
+    }
+    free(f64); free(dep);
+    return 1;
+}

@@ -1,0 +1,69 @@
+"""Generate tests/golden/* from the UNMODIFIED reference (oracle/_ref).
+
+Run in the build container (needs oracle/_ref, i.e. /root/reference at build
+time):   python tests/golden/make_golden.py
+
+For every case of tests/scenes.py it stores
+  <key>.ndsf.gz   the flat scene produced by ndt_b200_flatten from the
+                  reference's own scene + kd-tree structures (the INPUT), and
+  golden.json     SHA-256 digests of what the reference itself rendered for it:
+                  fp64 RGBA framebuffer of render_image (ndt.c:900), 8-bit
+                  image through pixel_d2c, and the primary-ray hit / object-id
+                  buffers from camera_target_point + trace_kd; plus a few raw
+                  sample pixels so a digest mismatch can be localised.
+The reference has no golden vectors of its own; these
+digests are the pin for oracle/ndt_oracle.c on boxes without /root/reference.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import ndt_b200  # noqa: E402
+from oracle.refharness import RefHarness, rgba_f64_to_u8  # noqa: E402
+from scenes import CASES  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    R = RefHarness()
+    out = {}
+    for c in CASES:
+        R.open_scene(c.scene)
+        frames = R.scene_frames(c.dims, c.cfg) if c.scene else 300
+        if frames <= 0:
+            frames = 300
+        R.begin_frame(c.dims, c.frame, frames, c.cfg)
+        flat = ndt_b200.flatten(R.scene_ptr, R.kdtree_ptr, c.w, c.h, 128, 1, R.get_bounds_ptr)
+        img, _ = R.render(c.w, c.h, threads=os.cpu_count())
+        hit, oid, dist = R.primary(c.w, c.h)
+        R.end_frame()
+        flat.save(os.path.join(HERE, c.key + ".ndsf.gz"))
+        u8 = rgba_f64_to_u8(img)
+        pts = [(0, 0), (c.h // 2, c.w // 2), (c.h - 1, c.w - 1), (c.h // 3, (2 * c.w) // 3)]
+        out[c.key] = {
+            "scene": c.scene, "dims": c.dims, "cfg": c.cfg, "frame": c.frame, "w": c.w, "h": c.h,
+            "flat_bytes": len(flat), "n_items": flat.header.n_items, "n_objects": flat.header.n_objects,
+            "n_nodes": flat.header.n_nodes, "n_leaf_refs": flat.header.n_leaf_refs,
+            "sha_f64": sha(img), "sha_u8": sha(u8), "sha_hit": sha(hit), "sha_id": sha(oid),
+            "hit_pixels": int(hit.sum()),
+            "samples": [{"y": y, "x": x, "rgba_hex": [float(v).hex() for v in img[y, x]],
+                         "hit": int(hit[y, x]), "id": int(oid[y, x])} for y, x in pts],
+        }
+        print(c.key, "flat", len(flat), "hit px", int(hit.sum()), flush=True)
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
