@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric: Mrays/s = unique nearest-hit queries (trace_kd calls, object.c:683:
+primary + reflection/refraction + shadow) per second; frames/s is reported next
+to it.  Workload: BASELINE config 2 -- scenes/hypercube.c at 8 dimensions,
+1920x1080, reflections on, frame 0 -- which is the configuration the metric is
+quoted on and fits one GPU.  The scene enters as the flat blob the struct-ABI
+adapter produced from the reference's own scene + kd-tree (tests/golden/, made
+by tests/golden/make_golden.py), so nothing under oracle/ runs on our arm.
+
+A STEP renders FRAMES_PER_GPU frames per GPU, each as TILES_PER_FRAME row bands
+(work items).  With N>1 the items of a step are pulled from one shared counter
+(dynamic tile queue) and finished tiles are gathered to rank 0 with NCCL
+send/recv; per-GPU work is fixed as N grows ("weak").
+
+  value  device-resident: scene already in HBM, outputs stay in HBM (rank 0's).
+  e2e    N=1: ndt_b200_upload + ndt_b200_render_tile with HOST buffers (scene
+         H2D and image D2H inside the timed region).  N>1: upload + device
+         render + NCCL gather + rank 0's D2H of every frame.
+  roofline  FP64 pipe: algorithmic flops of a step (counting build, untimed)
+         / CUDA-event kernel time, against the NON-FUSED DMUL+DADD peak measured
+         live (parity forbids FMA contraction); the DFMA peak is quoted too.
+  cpu_baseline / --impl reference: the UNMODIFIED reference's render_image
+         (oracle/_ref) on all host cores, on a bounded sample of the same
+         workload (same scene and frame at 1/16 of the pixels).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # key: (golden flat scene, width, height, description, reference scene plugin, dims, cfg, frame)
+    "config2": ("config2_hypercube8d", 1920, 1080,
+                "BASELINE config 2: scenes/hypercube.c -d 8, 1920x1080, reflections on, frame 0 "
+                "(6561 objects: sphere/cylinder/orthotope/hcylinder + hplane floor, kd 513 nodes)",
+                "hypercube", 8, None, 0),
+    "config1": ("config1_default4d", 1920, 1080,
+                "BASELINE config 1: built-in scene -d 4, 1920x1080, frame 0",
+                None, 4, None, 0),
+    "config4": ("config4_balls5d", 3840, 2160,
+                "BASELINE config 4: scenes/balls.c -d 5, 4K, frame 2", "balls", 5, None, 2),
+    "config5": ("config5_mixed10d", 1920, 1080,
+                "BASELINE config 5 (C twin): mixed10d -d 10, 1920x1080, frame 0", "mixed10d", 10, None, 0),
+}
+FRAMES_PER_GPU = 2
+TILES_PER_FRAME = 4
+SAMPLE_DIV = 4          # reference sample: width/4 x height/4 = 1/16 of the pixels
+
+
+def load_flat(key, w, h):
+    import ndt_b200
+    f = ndt_b200.FlatScene.load(os.path.join(ROOT, "tests", "golden", key + ".ndsf.gz"))
+    return f.retarget(w, h)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference on the host cores
+# --------------------------------------------------------------------------------------
+def reference_sample(workload, steps, warmup):
+    """Times render_image (ndt.c:900) of oracle/_ref on the bounded sample; returns a dict."""
+    from oracle import refharness
+    key, W, H, desc, scene, dims, cfg, frame = WORKLOADS[workload]
+    sw, sh = W // SAMPLE_DIV, H // SAMPLE_DIV
+    cores = os.cpu_count()
+    if not refharness.available():
+        raise RuntimeError("oracle/_ref missing: run `make -C oracle ref` in the build container")
+    R = refharness.RefHarness()
+    R.open_scene(scene)
+    frames = R.scene_frames(dims, cfg) if scene else 300
+    times = []
+    for i in range(warmup + steps):
+        R.begin_frame(dims, frame, frames if frames > 0 else 300, cfg)
+        try:
+            _, sec = R.render(sw, sh, threads=cores)
+        finally:
+            R.end_frame()
+        if i >= warmup:
+            times.append(sec)
+    # unique / as-executed ray counts of the sample, from the oracle port (one trace per pixel)
+    import ndt_b200
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libndt_oracle.so"))
+    L.ndo_render.argtypes = [C.c_char_p] + [C.c_int] * 5 + [C.c_void_p] * 6
+    flat = load_flat(key, sw, sh)
+    st = (C.c_uint64 * 5)()
+    L.ndo_render(flat.blob, 0, 0, sw, sh, cores, None, None, None, None, None, st)
+    uniq = st[0] + st[1] + st[2]
+    sec = float(np.mean(times))
+    return {"seconds_per_step": sec, "rays_unique": int(uniq), "rays_ref": int(st[3]),
+            "mrays_unique": uniq / sec / 1e6, "mrays_ref": st[3] / sec / 1e6,
+            "frames_per_s_full": 1.0 / (sec * SAMPLE_DIV * SAMPLE_DIV),
+            "cores": cores, "sample": f"same scene/frame at {sw}x{sh} (1/{SAMPLE_DIV*SAMPLE_DIV} of the pixels), "
+                                      f"render_image only (kd build excluded), {cores} pthreads, mean of {steps}",
+            "kd_build_seconds": R.kd_seconds}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    key, W, H, desc, *_ = WORKLOADS[args.workload]
+    try:
+        r = reference_sample(args.workload, args.steps, args.warmup)
+    except Exception as e:  # the oracle always exists in a built tree; say why if not
+        print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+        return
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": r["mrays_unique"], "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "note": "CPU: unmodified reference render_image on host cores"},
+        "frames_per_s": r["frames_per_s_full"],
+        "rays": {"unique_per_step": r["rays_unique"], "as_executed_by_reference_per_step": r["rays_ref"],
+                 "mrays_as_executed": r["mrays_ref"]},
+        "cpu_baseline": {"value": r["mrays_unique"], "unit": "Mrays/s", "cores": r["cores"],
+                         "kind": "reference", "sample": r["sample"]},
+        "e2e": {"value": r["mrays_unique"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import ndt_b200
+    from ndt_b200 import multi
+
+    key, W, H, desc, *_ = WORKLOADS[args.workload]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    flat = load_flat(key, W, H)
+    ctx = ndt_b200.Context(local_rank)
+    ctx.upload(flat)
+
+    n_frames = FRAMES_PER_GPU * world
+    band = (H + TILES_PER_FRAME - 1) // TILES_PER_FRAME
+    items = [(f, t * band, min(band, H - t * band)) for f in range(n_frames) for t in range(TILES_PER_FRAME)]
+    queue = multi.TileQueue(dist, rank, world)
+    # rank 0 holds every frame of the step; other ranks a staging area for their own tiles
+    frames_dev = torch.zeros((n_frames, H, W, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+    stage = torch.zeros((len(items), band, W, 4), dtype=torch.uint8, device=dev) if world > 1 and rank != 0 else None
+    frames_host = torch.zeros((n_frames, H, W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    totals = {"rays": 0, "dev_ms": 0.0, "launches": 0}
+
+    def device_step(step_id, upload):
+        if upload:
+            ctx.upload(flat)
+        flush.fill_(step_id & 0xFF)                       # L2 flush between steps
+        torch.cuda.synchronize()
+        mine = []
+        for idx in queue.pull(step_id, len(items)):
+            f, y0, th = items[idx]
+            if rank == 0:
+                dst = frames_dev[f, y0:y0 + th]
+            else:
+                dst = stage[len(mine), :th]
+            ctx.launch_tile(0, y0, W, th, d_u8=dst.data_ptr())
+            st = ctx.sync()
+            totals["rays"] += st.rays_unique
+            totals["dev_ms"] += st.device_ms
+            totals["launches"] += st.launches
+            mine.append(idx)
+        if world > 1:
+            multi.gather_tiles(dist, rank, world, items, mine, stage, frames_dev, band)
+        return mine
+
+    def timed(fn, k, w):
+        for i in range(w):
+            fn(i)
+        barrier()
+        for kk in totals:
+            totals[kk] = 0
+        t0 = time.perf_counter()
+        for i in range(k):
+            fn(w + i)
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt, float(totals["rays"]), totals["dev_ms"], float(totals["launches"])],
+                             dtype=torch.float64, device=dev)
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return tmax[0].item(), tsum[1].item(), tmax[2].item(), tsum[3].item()
+        return dt, float(totals["rays"]), totals["dev_ms"], float(totals["launches"])
+
+    # ---- algorithmic flops of one step (counting build, untimed) and FP64 peaks ------------
+    flops_frame = 0
+    peak_nf = peak_f = None
+    if rank == 0:
+        ctx.set_options(ndt_b200.OPT_COUNT_FLOPS)
+        for t in range(TILES_PER_FRAME):
+            y0 = t * band
+            th = min(band, H - y0)
+            ctx.launch_tile(0, y0, W, th, d_u8=frames_dev[0, y0:y0 + th].data_ptr())
+            flops_frame += ctx.sync().flops
+        ctx.set_options(0)
+        peak_nf = ctx.fp64_peak(False)
+        peak_f = ctx.fp64_peak(True)
+
+    # ---- device-resident value ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dt, rays, dev_ms, launches = timed(lambda i: device_step(i, False), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    frames_total = n_frames * args.steps
+    value = rays / dt / 1e6
+
+    # ---- end to end -------------------------------------------------------------------------
+    h2d = len(flat)
+    if world == 1:
+        host = ndt_b200.Frame(W, band, ("u8",))
+        out_host = np.zeros((n_frames, H, W, 4), np.uint8)
+
+        def e2e_step(i):
+            ctx.upload(flat)                                # scene H2D from host memory
+            for f, y0, th in items:
+                fr = ndt_b200.Frame(W, th, ()) if th != band else host
+                if th != band:
+                    fr.rgba_u8 = np.empty((th, W, 4), np.uint8)
+                ctx.render_tile(0, y0, W, th, out=fr)       # C ABI, host buffers, D2H inside
+                totals["rays"] += fr.stats.rays_unique
+                totals["launches"] += fr.stats.launches
+                totals["dev_ms"] += fr.stats.device_ms
+                out_host[f, y0:y0 + th] = fr.rgba_u8
+        d2h = n_frames * H * W * 4
+    else:
+        def e2e_step(i):
+            device_step(i, True)
+            if rank == 0:
+                frames_host.copy_(frames_dev, non_blocking=True)
+                torch.cuda.synchronize()
+        d2h = n_frames * H * W * 4
+    edt, erays, _, _ = timed(e2e_step, args.steps, max(1, args.warmup // 2))
+    e2e_value = erays / edt / 1e6
+
+    if rank == 0:
+        flops_step = flops_frame * n_frames
+        kernel_s = dev_ms * 1e-3 / args.steps            # CUDA-event kernel time of one step (max over ranks)
+        achieved = flops_frame * FRAMES_PER_GPU / kernel_s / 1e12 if kernel_s > 0 else 0.0
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": peak_nf / 1e3, "unit": "TFLOP/s",
+            "frac": achieved / (peak_nf / 1e3) if peak_nf else None,
+            "traffic": None,
+            "kernel": "k_generation<8> (all generations of a step; share of step in profiles/)",
+            "algorithmic_flops_per_frame": flops_frame,
+            "peak_source": "measured live by ndt_b200_fp64_peak: non-fused DMUL+DADD chains on all SMs "
+                           "(MEASURED_PEAKS.json has no FP64 entry); parity forbids FMA contraction",
+            "peak_dfma_tflops": peak_f / 1e3, "frac_of_dfma_peak": achieved / (peak_f / 1e3) if peak_f else None,
+            "kernel_ms_per_step_per_gpu": kernel_s * 1e3,
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = reference_sample(args.workload, 1, 0)
+                cpu = {"value": r["mrays_unique"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
+                       "sample": r["sample"], "frames_per_s": r["frames_per_s_full"],
+                       "mrays_as_executed_by_reference": r["mrays_ref"]}
+            except Exception as e:
+                cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference",
+                       "sample": "unavailable: " + str(e)[:160]}
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "frames_per_step": n_frames, "tiles_per_frame": TILES_PER_FRAME,
+                       "parallelism": f"dynamic tile queue over {world} GPU(s), NCCL gather to rank 0",
+                       "l2": "256 MiB fill between steps (inside the bracket); the 3.4 MB scene is meant to be "
+                             "L2-resident within a step",
+                       "rays": "unique trace_kd-equivalent queries (primary+bounce+shadow)"},
+            "frames_per_s": frames_total / dt,
+            "rays_per_frame": rays / frames_total,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "frames_per_s": frames_total / edt,
+                    "path": "ndt_b200_upload + ndt_b200_render_tile (host buffers)" if world == 1 else
+                            "upload + device render + NCCL gather + rank-0 D2H"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
