@@ -56,8 +56,8 @@ WORKLOADS = {
     "config5": ("config5_mixed10d", 1920, 1080,
                 "BASELINE config 5 (C twin): mixed10d -d 10, 1920x1080, frame 0", "mixed10d", 10, None, 0),
 }
-FRAMES_PER_GPU = 2
-TILES_PER_FRAME = 4
+FRAMES_PER_GPU = 4
+TILES_PER_FRAME = 1
 SAMPLE_DIV = 4          # reference sample: width/4 x height/4 = 1/16 of the pixels
 
 
@@ -370,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))

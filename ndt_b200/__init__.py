@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libndt_b200.so")
+LIB_PATH = os.environ.get("NDT_B200_LIB") or os.path.join(_HERE, "libndt_b200.so")
 
 OPT_COUNT_FLOPS = 1
 

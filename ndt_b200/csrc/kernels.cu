@@ -30,6 +30,15 @@
 using namespace ndt;
 
 #define BLOCK 128
+#ifndef NDT_MIN_BLOCKS
+#define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
+#endif
+/* experiments: -DNDT_ONLY_NP=8 instantiates a single dimension (fast builds) */
+#ifdef NDT_ONLY_NP
+#define NDT_HAVE_NP(n) ((n) == NDT_ONLY_NP)
+#else
+#define NDT_HAVE_NP(n) 1
+#endif
 
 struct GenArgs {
     int gen;                 /* 0: rays are generated from pixels */
@@ -51,7 +60,7 @@ struct GenArgs {
 };
 
 template <int NP, bool CNT>
-__global__ void __launch_bounds__(BLOCK) k_generation(const Scene sc, const GenArgs a)
+__global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scene sc, const GenArgs a)
 {
     const int lane = threadIdx.x & 31;
     Mailbox mb;
@@ -288,13 +297,9 @@ static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
     int &g = c->grid_blocks[cnt ? 1 : 0][np / 2];
     if (g == 0) {
         int b = 1;
-        switch (np) {
-        case 4:  b = cnt ? blocks_per_sm<4, true>()  : blocks_per_sm<4, false>();  break;
-        case 6:  b = cnt ? blocks_per_sm<6, true>()  : blocks_per_sm<6, false>();  break;
-        case 8:  b = cnt ? blocks_per_sm<8, true>()  : blocks_per_sm<8, false>();  break;
-        case 10: b = cnt ? blocks_per_sm<10, true>() : blocks_per_sm<10, false>(); break;
-        case 12: b = cnt ? blocks_per_sm<12, true>() : blocks_per_sm<12, false>(); break;
-        }
+#define OCC(N) case N: if (NDT_HAVE_NP(N)) b = cnt ? blocks_per_sm<N, true>() : blocks_per_sm<N, false>(); break
+        switch (np) { OCC(4); OCC(6); OCC(8); OCC(10); OCC(12); }
+#undef OCC
         g = b * c->sm_count;
     }
     return g;
@@ -302,14 +307,8 @@ static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
 
 static void dispatch_generation(int np, bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
 {
-#define GO(N) do { if (cnt) launch_generation<N, true>(blocks, st, sc, a); else launch_generation<N, false>(blocks, st, sc, a); } while (0)
-    switch (np) {
-    case 4: GO(4); break;
-    case 6: GO(6); break;
-    case 8: GO(8); break;
-    case 10: GO(10); break;
-    case 12: GO(12); break;
-    }
+#define GO(N) case N: if (NDT_HAVE_NP(N)) { if (cnt) launch_generation<N, true>(blocks, st, sc, a); else launch_generation<N, false>(blocks, st, sc, a); } break
+    switch (np) { GO(4); GO(6); GO(8); GO(10); GO(12); }
 #undef GO
 }
 

@@ -57,7 +57,7 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
 {
     const int n = sc.n;
     const int nl = sc.n_lights;
-    Hit<NP> H;                    /* the ray's own hit */
+    double Hp[NP], Hn[NP];        /* the ray's own hit point and normal */
     double clr0 = 0, clr1 = 0, clr2 = 0;
     double hr = 0, hg = 0, hb = 0;        /* colour */
     double rr = 0, rg = 0, rb = 0;        /* reflectivity used for specular */
@@ -96,25 +96,25 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
             if (ltype == NDT_L_DIRECTIONAL) {
                 vload<NP>(rev_light, lv + 2 * NP);                  /* unit(-dir), hoisted */
             } else {
-                vsub<NP>(lgt_pos, H.p, rev_light);
+                vsub<NP>(lgt_pos, Hp, rev_light);
                 vunit<NP>(rev_light);
             }
             double rev_view[NP];
-            vsub<NP>(src, H.p, rev_view);
-            double d1 = vdot<NP>(rev_light, H.nrm);
-            double d2 = vdot<NP>(rev_view, H.nrm);
+            vsub<NP>(src, Hp, rev_view);
+            double d1 = vdot<NP>(rev_light, Hn);
+            double d2 = vdot<NP>(rev_view, Hn);
             tally.add(8 * n + 2);
             if ((d1 * d2) <= 0) continue;
             if (ltype == NDT_L_DIRECTIONAL) {                       /* ndt.c:230-240 */
                 NDT_UNROLL
-                for (int i = 0; i < NP; ++i) ro[i] = NDT_LDG(lv + 3 * NP + i) + H.p[i];
+                for (int i = 0; i < NP; ++i) ro[i] = NDT_LDG(lv + 3 * NP + i) + Hp[i];
                 vcopy<NP>(rv, rev_light);
                 limit = 0.0;
                 ldist2 = 1.0;
             } else {                                                /* ndt.c:184-211 */
-                limit = vdist<NP>(H.p, lgt_pos);
+                limit = vdist<NP>(Hp, lgt_pos);
                 limit += EPS;
-                vsub<NP>(H.p, lgt_pos, light_vec);
+                vsub<NP>(Hp, lgt_pos, light_vec);
                 ldist2 = vdot<NP>(light_vec, light_vec);
                 vunit<NP>(light_vec);
                 tally.add(9 * n + 2);
@@ -130,17 +130,16 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
             ++n_shadow;
         }
 
-        Hit<NP> T;
+        Hit T;
         trace_kd<NP, CNT>(sc, mb, ro, rv, limit, T, overflow, tally);
 
         if (it < 0) {
             /* ndt.c:357-376 */
-            H = T;
             oid = T.id;
             double trace_dist = -1;
             if (oid >= 0) {
-                if (!T.found) { /* object reported without a hit cannot happen: ptr is set on accept only */ }
-                trace_dist = vdist<NP>(H.p, src);
+                materialise<NP>(sc, T.win, ro, rv, Hp, Hn);
+                trace_dist = vdist<NP>(Hp, src);
                 tally.add(3 * n);
             }
             prim_id = oid;
@@ -164,16 +163,17 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
         if (ltype == NDT_L_DIRECTIONAL) {
             if (T.found) continue;
             vload<NP>(light_vec, sc.geom + NDT_LDG(&L->vec_off) + NP);   /* ndt.c:252 */
-            vcopy<NP>(lhn, H.nrm);
+            vcopy<NP>(lhn, Hn);
         } else {
             if (!T.found || T.id != oid) continue;
-            double dist = vdist<NP>(H.p, T.p);
+            double lhp[NP];
+            materialise<NP>(sc, T.win, ro, rv, lhp, lhn);
+            double dist = vdist<NP>(Hp, lhp);
             tally.add(3 * n);
             if (dist > EPS) continue;
-            vcopy<NP>(lhn, T.nrm);
         }
         const double lr = NDT_LDG(&L->rgb[0]), lg = NDT_LDG(&L->rgb[1]), lb = NDT_LDG(&L->rgb[2]);
-        double angle = vangle<NP>(H.nrm, light_vec);
+        double angle = vangle<NP>(Hn, light_vec);
         if (angle > PI / 2.0) angle = PI - angle;
         double light_scale = cos(angle) / ldist2;
         tally.add(6 * n + 8);
@@ -213,7 +213,7 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
     /* children: ndt.c:383-429 */
     const double h0 = rec.h[0], h1 = rec.h[1], h2 = rec.h[2];
     const double contrib = ref_max(h0, ref_max(h1, h2));
-    vcopy<NP>(sp.origin, H.p);
+    vcopy<NP>(sp.origin, Hp);
     if (contrib > 0) {
         if (h0 != 0.0 || h1 != 0.0 || h2 != 0.0) {
             sp.refl_frac = contrib * frac;
@@ -221,7 +221,7 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
                 sp.want_refl = 2;
             } else {
                 sp.want_refl = 1;
-                vreflect<NP>(look, H.nrm, sp.refl_dir, 1.0);
+                vreflect<NP>(look, Hn, sp.refl_dir, 1.0);
                 vunit<NP>(sp.refl_dir);
                 tally.add(10 * n + 4);
             }
@@ -233,7 +233,7 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
             sp.want_refr = 2;
         } else {
             sp.want_refr = 1;
-            vrefract<NP>(look, H.nrm, sp.refr_dir, NDT_LDG(&(sc.obj + oid)->refract_index));
+            vrefract<NP>(look, Hn, sp.refr_dir, NDT_LDG(&(sc.obj + oid)->refract_index));
             vunit<NP>(sp.refr_dir);
             tally.add(30 * n + 20);
         }
