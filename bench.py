@@ -223,7 +223,11 @@ def run_ours(args, rank, world, local_rank):
 
     totals = {"rays": 0, "dev_ms": 0.0, "launches": 0}
 
-    def device_step(step_id, upload):
+    serial = [0]
+
+    def device_step(_unused, upload):
+        step_id = serial[0]                               # queue keys must never repeat within a job
+        serial[0] += 1
         if upload:
             ctx.upload(flat)
         flush.fill_(step_id & 0xFF)                       # L2 flush between steps
