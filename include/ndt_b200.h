@@ -132,6 +132,16 @@ int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_a
                           int aa_depth, int max_optic_depth, int specular,
                           void *img_copy, void *depth_copy);
 
+/* trace_kd (object.c:683) for n_rays explicit rays: origins/dirs are n_rays x N
+ * doubles (row-major, HOST), dist_limits may be NULL (= -1.0, "check all
+ * objects", ndt.c:172-183).  Outputs per ray: trace_kd's return value, the id
+ * of the object it reported (-1 = NULL), the accepted distance, the hit point
+ * and the normal exactly as the plugin returned it (not normalised).  This is
+ * the probe the per-primitive known-answer tests use. */
+int ndt_b200_trace_rays(ndt_b200_ctx *ctx, int n_rays, const double *origins, const double *dirs,
+                        const double *dist_limits, int32_t *found, int32_t *obj_id,
+                        double *t, double *hit, double *normal);
+
 /* one FP64 pipe probe: returns sustained GFLOP/s of an all-SM chain of
  * dependent-free DFMA (fused=1) or DMUL+DADD pairs (fused=0); the roofline
  * denominators of bench.py */

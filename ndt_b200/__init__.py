@@ -89,6 +89,7 @@ def lib():
     L.ndt_b200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.ndt_b200_stream.argtypes = [C.c_void_p]
     L.ndt_b200_stream.restype = C.c_void_p
+    L.ndt_b200_trace_rays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     L.ndt_b200_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ndt_b200_render_image.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_HostApi), C.c_char_p, C.c_char_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -120,9 +121,12 @@ class FlatScene:
 
     def save(self, path):
         import gzip
-        op = gzip.open if str(path).endswith(".gz") else open
-        with op(path, "wb") as f:
-            f.write(self.blob)
+        if str(path).endswith(".gz"):
+            with open(path, "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0, filename="") as f:
+                f.write(self.blob)        # mtime=0: byte-identical files for identical scenes
+        else:
+            with open(path, "wb") as f:
+                f.write(self.blob)
 
     def retarget(self, width, height):
         """The same scene for another frame size is NOT a header edit: the camera
@@ -223,6 +227,18 @@ class Context:
     @property
     def stream(self):
         return lib().ndt_b200_stream(self._h)
+
+    def trace_rays(self, origins, dirs, dist_limits=None):
+        """ndt_b200_trace_rays: returns (found, obj_id, t, hit, normal) numpy arrays."""
+        o = np.ascontiguousarray(origins, np.float64)
+        v = np.ascontiguousarray(dirs, np.float64)
+        n = o.shape[0]
+        lim = None if dist_limits is None else np.ascontiguousarray(dist_limits, np.float64)
+        found = np.zeros(n, np.int32); oid = np.zeros(n, np.int32); t = np.zeros(n, np.float64)
+        hit = np.zeros_like(o); nrm = np.zeros_like(o)
+        _check(lib().ndt_b200_trace_rays(self._h, n, o.ctypes.data, v.ctypes.data, _p(lim), found.ctypes.data,
+                                         oid.ctypes.data, t.ctypes.data, hit.ctypes.data, nrm.ctypes.data))
+        return found, oid, t, hit, nrm
 
     def fp64_peak(self, fused):
         g = C.c_double(0)

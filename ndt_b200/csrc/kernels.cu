@@ -226,6 +226,41 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
     }
 }
 
+/* trace_kd (object.c:683) for an explicit list of rays: the probe behind
+ * ndt_b200_trace_rays, used by the per-primitive known-answer tests */
+template <int NP>
+__global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS)
+k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in, const double *limits,
+             int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
+             uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow)
+{
+    Mailbox mb;
+    mb.bits = mb_bits; mb.stride = mb_stride;
+    mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
+    mb.words = mb_words; mb.group_shift = mb_shift;
+    mb.dirty = ~0ull;
+    Tally<false> tally;
+    int ovf = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += gridDim.x * blockDim.x) {
+        double o[NP], v[NP];
+        NDT_UNROLL
+        for (int i = 0; i < NP; ++i) {
+            o[i] = i < sc.n ? o_in[(size_t)r * sc.n + i] : 0.0;
+            v[i] = i < sc.n ? v_in[(size_t)r * sc.n + i] : 0.0;
+        }
+        Hit T;
+        trace_kd<NP, false>(sc, mb, o, v, limits ? limits[r] : -1.0, T, ovf, tally);
+        double p[NP], nr[NP];
+        vzero<NP>(p); vzero<NP>(nr);
+        if (T.id >= 0) materialise<NP>(sc, T.win, o, v, p, nr);
+        found[r] = T.found;
+        ids[r] = T.id;
+        ts[r] = T.t;
+        for (int i = 0; i < sc.n; ++i) { hits[(size_t)r * sc.n + i] = p[i]; normals[(size_t)r * sc.n + i] = nr[i]; }
+    }
+    if (ovf) atomicExch(overflow + 1, 1);
+}
+
 /* FP64 pipe probe: 8 independent chains per thread */
 template <bool FUSED> __global__ void k_fp64_probe(double *sink, int iters)
 {
@@ -605,6 +640,55 @@ extern "C" int ndt_b200_render_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     if (r) return r;
     c->last = acc;
     if (stats) *stats = acc;
+    return 0;
+}
+
+extern "C" int ndt_b200_trace_rays(ndt_b200_ctx *c, int n_rays, const double *origins, const double *dirs,
+                                   const double *dist_limits, int32_t *found, int32_t *obj_id,
+                                   double *t, double *hit, double *normal)
+{
+    if (!c || n_rays < 0 || !origins || !dirs || !found || !obj_id || !t || !hit || !normal)
+        return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_trace_rays: NULL argument");
+    if (!c->have_scene) return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_trace_rays before ndt_b200_upload");
+    if (n_rays == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const ndt_flat_header &h = c->hdr;
+    const int np = h.npad, n = h.n;
+    int blocks = (n_rays + BLOCK - 1) / BLOCK;
+    if (blocks > c->sm_count * 2) blocks = c->sm_count * 2;
+    int r = ensure_pools(c, 32, np, blocks * BLOCK);
+    if (r) return r;
+    const size_t vb = (size_t)n_rays * n * sizeof(double);
+    const size_t total = 4 * vb + (size_t)n_rays * (2 * sizeof(double) + 2 * sizeof(int32_t)) + 256;
+    char *d = NULL;
+    CK(cudaMalloc(&d, total));
+    double *d_o = (double *)d, *d_v = d_o + (size_t)n_rays * n, *d_hit = d_v + (size_t)n_rays * n,
+           *d_nrm = d_hit + (size_t)n_rays * n, *d_lim = d_nrm + (size_t)n_rays * n, *d_t = d_lim + n_rays;
+    int32_t *d_found = (int32_t *)(d_t + n_rays), *d_id = d_found + n_rays;
+    cudaStream_t st = c->stream;
+    cudaError_t e = cudaMemcpyAsync(d_o, origins, vb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, dirs, vb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && dist_limits) e = cudaMemcpyAsync(d_lim, dist_limits, n_rays * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_ctr, 0, 4 * sizeof(int), st);
+    uint32_t words = (uint32_t)((h.n_items + 31) / 32); if (!words) words = 1;
+    uint32_t shift = 0; while ((words >> shift) >= 64) ++shift;
+    if (e == cudaSuccess) {
+#define TR(N) case N: if (NDT_HAVE_NP(N)) k_trace_rays<N><<<blocks, BLOCK, 0, st>>>(c->sc, n_rays, d_o, d_v, dist_limits ? d_lim : NULL, \
+        d_found, d_id, d_t, d_hit, d_nrm, c->d_mb, (uint32_t)(blocks * BLOCK), words, shift, c->d_ctr + 2); break
+        switch (np) { TR(4); TR(6); TR(8); TR(10); TR(12); }
+#undef TR
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(found, d_found, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(obj_id, d_id, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t, d_t, n_rays * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hit, d_hit, vb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(normal, d_nrm, vb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_ctr, c->d_ctr, 4 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return ndt_set_error(NDT_B200_E_CUDA, "ndt_b200_trace_rays: %s", cudaGetErrorString(e));
+    if (c->h_ctr[3]) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
     return 0;
 }
 

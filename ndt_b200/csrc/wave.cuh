@@ -56,7 +56,11 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
                         uint32_t &n_shadow, int &overflow, Tally<CNT> &tally)
 {
     const int n = sc.n;
+#ifdef NDT_EXP_NO_LIGHTS
+    const int nl = 0;             /* experiment: extend-only kernel (register / time budget of the trace) */
+#else
     const int nl = sc.n_lights;
+#endif
     double Hp[NP], Hn[NP];        /* the ray's own hit point and normal */
     double clr0 = 0, clr1 = 0, clr2 = 0;
     double hr = 0, hg = 0, hb = 0;        /* colour */
@@ -131,7 +135,7 @@ NDT_FN void process_ray(const Scene &sc, Mailbox &mb, const double *src, const d
         }
 
         Hit T;
-        trace_kd<NP, CNT>(sc, mb, ro, rv, limit, T, overflow, tally);
+        trace_kd<NP, CNT>(sc, mb, ro, rv, limit, T, overflow, tally, ltype == NDT_L_DIRECTIONAL);
 
         if (it < 0) {
             /* ndt.c:357-376 */
