@@ -193,6 +193,9 @@ class Context:
         self.close()
 
     def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():
+            return      # the CUDA runtime may already be gone at interpreter shutdown
         try:
             self.close()
         except Exception:
