@@ -132,6 +132,16 @@ int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_a
                           int aa_depth, int max_optic_depth, int specular,
                           void *img_copy, void *depth_copy);
 
+/* Drop-in for kd_tree_build(kd_tree_t*, kd_item_list_t*) (kd-tree.c:421-477),
+ * the serial pre-pass in front of the render path (ndt.c:1908; 10-13 s per
+ * frame for BASELINE config 2).  Same arguments, same result: the reference's
+ * own kd_tree_t in host memory, node for node and bit for bit (the exhaustive
+ * split search of kd-tree.c:315-345 runs on the GPU, one thread per candidate
+ * plane).  `kd_tree` must have been initialised with kd_tree_init.  Returns
+ * what kd_tree_build returns (1: the root stayed a leaf, 0: it was split) or
+ * a negative status. */
+int ndt_b200_kd_tree_build(void *kd_tree, void *kd_item_list);
+
 /* trace_kd (object.c:683) for n_rays explicit rays: origins/dirs are n_rays x N
  * doubles (row-major, HOST), dist_limits may be NULL (= -1.0, "check all
  * objects", ndt.c:172-183).  Outputs per ray: trace_kd's return value, the id

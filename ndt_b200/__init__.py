@@ -89,6 +89,7 @@ def lib():
     L.ndt_b200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.ndt_b200_stream.argtypes = [C.c_void_p]
     L.ndt_b200_stream.restype = C.c_void_p
+    L.ndt_b200_kd_tree_build.argtypes = [C.c_void_p, C.c_void_p]
     L.ndt_b200_trace_rays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     L.ndt_b200_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ndt_b200_render_image.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_HostApi), C.c_char_p, C.c_char_p,
@@ -155,6 +156,11 @@ def flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth=128, specular=
         return FlatScene(C.string_at(out.value, total))
     finally:
         L.ndt_b200_free_flat(out)
+
+
+def kd_tree_build(kd_tree_ptr, kd_item_list_ptr):
+    """ndt_b200_kd_tree_build: drop-in for kd_tree_build (kd-tree.c:421) on host structures."""
+    return _check(lib().ndt_b200_kd_tree_build(kd_tree_ptr, kd_item_list_ptr))
 
 
 class Frame:

@@ -1,0 +1,296 @@
+/*
+ * kdbuild.cu -- drop-in for kd_tree_build (kd-tree.c:421-477), the serial
+ * bottleneck in front of the render path (10-13 s per
+ * frame for BASELINE config 2 on one host core).
+ *
+ * The reference builder is exhaustive: at every node it scores every
+ * candidate plane (each dimension x each item x {lower-2EPS, upper+2EPS}) by
+ * counting the node's items left / right / straddling (kdtree_split_score,
+ * kd-tree.c:294-313) and keeps the first best (strict >, kd-tree.c:323-345).
+ * That is 2*D*n^2 comparisons per node -- 1.4e9 at the root of config 2 -- and
+ * embarrassingly parallel.  Here one GPU thread owns one candidate and streams
+ * the node's item intervals through shared memory; a block reduction keeps
+ * (best score, lowest candidate index), the host picks the winner among the
+ * per-block results, partitions the item list exactly like
+ * kd_tree_split_node (kd-tree.c:381-403: order preserved, straddlers to both
+ * sides, infinite objects dropped) and recurses.  Nodes with few items are
+ * scored on the host with the same comparisons.
+ *
+ * The result is the reference's own `kd_tree_t` in host memory (calloc'ed
+ * nodes, leaf id/pointer arrays, root AABB, infinite-object list), bit for bit
+ * what kd_tree_build produces, so everything downstream -- including the
+ * reference's CPU renderer and kd_tree_free -- keeps working.  Tie-breaking of
+ * the render path depends on the tree shape (SURVEY note 5); the test compares
+ * the flattened trees byte for byte.
+ */
+#include <cuda_runtime.h>
+#include <float.h>
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+#include "ndt_abi.h"
+#include "ndt_internal.h"
+
+#define EPS NDT_EPS
+#define KD_GPU_MIN_ITEMS 48      /* below this the host scores the node itself */
+#define KD_BLOCK 256
+
+/* kd-tree.h:22-26, 40-43 */
+typedef struct {
+    ndtabi_vec lower, upper;
+    int id;
+    void *obj_ptr;
+} kdb_item;
+typedef struct {
+    kdb_item **items;
+    int n, cap;
+} kdb_item_list;
+
+struct Best {
+    int score;      /* integer valued in the reference too (kd-tree.c:311) */
+    int cand;       /* (dim*n + i)*2 + side; lower wins ties = first best */
+};
+
+__device__ __forceinline__ bool better(const Best &a, const Best &b)
+{
+    return a.score > b.score || (a.score == b.score && a.cand < b.cand);
+}
+
+/* one thread per candidate plane of one node */
+__global__ void __launch_bounds__(KD_BLOCK)
+k_kd_score(const double *__restrict__ lo, const double *__restrict__ hi, int n_total,
+           const int *__restrict__ list, int n, int dims, Best *block_best)
+{
+    __shared__ double s_lo[KD_BLOCK], s_hi[KD_BLOCK];
+    __shared__ Best s_best[KD_BLOCK / 32];
+    const int per_dim = 2 * n;
+    const int blocks_per_dim = (per_dim + KD_BLOCK - 1) / KD_BLOCK;
+    const int d = blockIdx.x / blocks_per_dim;
+    const int c = (blockIdx.x % blocks_per_dim) * KD_BLOCK + threadIdx.x;   /* candidate within the dimension */
+    const bool live = c < per_dim;
+    const double *dlo = lo + (size_t)d * n_total, *dhi = hi + (size_t)d * n_total;
+    double pos = 0.0;
+    if (live) {
+        const int it = list[c >> 1];
+        pos = (c & 1) ? dhi[it] + 2 * EPS : dlo[it] - 2 * EPS;              /* kd-tree.c:328,336 */
+    }
+    const double pl = pos - EPS, pr = pos + EPS;
+    int left = 0, right = 0;
+    for (int base = 0; base < n; base += KD_BLOCK) {
+        const int j = base + threadIdx.x;
+        if (j < n) { const int it = list[j]; s_lo[threadIdx.x] = dlo[it]; s_hi[threadIdx.x] = dhi[it]; }
+        __syncthreads();
+        const int m = min(KD_BLOCK, n - base);
+        if (live) {
+            for (int k = 0; k < m; ++k) {                                   /* kd-tree.c:304-309 */
+                const double il = s_lo[k], iu = s_hi[k];
+                if (iu < pl) ++left;
+                else if (il > pr) ++right;
+            }
+        }
+        __syncthreads();
+    }
+    Best b;
+    b.score = INT_MIN; b.cand = INT_MAX;
+    if (live && left > 0 && right > 0) {
+        const int unsplit = n - left - right;
+        b.score = n - (abs(left - right) + 2 * unsplit);
+        b.cand = (d * n + (c >> 1)) * 2 + (c & 1);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        Best t;
+        t.score = __shfl_down_sync(0xffffffffu, b.score, o);
+        t.cand = __shfl_down_sync(0xffffffffu, b.cand, o);
+        if (better(t, b)) b = t;
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < KD_BLOCK / 32; ++w) if (better(s_best[w], b)) b = s_best[w];
+        block_best[blockIdx.x] = b;
+    }
+}
+
+struct Builder {
+    int dims, n_total;
+    kdb_item **items;            /* all items, index = id */
+    double *h_lo, *h_hi;         /* [dims][n_total] */
+    double *d_lo, *d_hi;
+    int *d_list; Best *d_best; Best *h_best;
+    size_t list_cap, best_cap;
+    cudaStream_t st;
+    int gpu_nodes, host_nodes, total_nodes;
+    const char *err;
+};
+
+/* the reference's search on the host, same comparisons (small nodes) */
+static bool host_search(const Builder &B, const int *list, int n, int *out_dim, double *out_pos)
+{
+    bool found = false;
+    int best = INT_MIN;
+    for (int d = 0; d < B.dims; ++d) {
+        const double *lo = B.h_lo + (size_t)d * B.n_total, *hi = B.h_hi + (size_t)d * B.n_total;
+        for (int i = 0; i < n; ++i) {
+            for (int side = 0; side < 2; ++side) {
+                const double pos = side ? hi[list[i]] + 2 * EPS : lo[list[i]] - 2 * EPS;
+                int left = 0, right = 0;
+                for (int j = 0; j < n; ++j) {
+                    const double il = lo[list[j]], iu = hi[list[j]];
+                    if (iu < pos - EPS) ++left;
+                    else if (il > pos + EPS) ++right;
+                }
+                if (left > 0 && right > 0) {
+                    const int score = n - (abs(left - right) + 2 * (n - left - right));
+                    if (score > best) { best = score; *out_dim = d; *out_pos = pos; found = true; }
+                }
+            }
+        }
+    }
+    return found;
+}
+
+static bool gpu_search(Builder &B, const int *list, int n, int *out_dim, double *out_pos)
+{
+    const int per_dim = 2 * n;
+    const int blocks_per_dim = (per_dim + KD_BLOCK - 1) / KD_BLOCK;
+    const int blocks = blocks_per_dim * B.dims;
+    if ((size_t)n > B.list_cap || (size_t)blocks > B.best_cap) { B.err = "kd build: scratch too small"; return false; }
+    cudaMemcpyAsync(B.d_list, list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, B.st);
+    k_kd_score<<<blocks, KD_BLOCK, 0, B.st>>>(B.d_lo, B.d_hi, B.n_total, B.d_list, n, B.dims, B.d_best);
+    cudaMemcpyAsync(B.h_best, B.d_best, (size_t)blocks * sizeof(Best), cudaMemcpyDeviceToHost, B.st);
+    cudaError_t e = cudaStreamSynchronize(B.st);
+    if (e != cudaSuccess) { B.err = cudaGetErrorString(e); return false; }
+    Best b; b.score = INT_MIN; b.cand = INT_MAX;
+    for (int k = 0; k < blocks; ++k) {
+        const Best &t = B.h_best[k];
+        if (t.score > b.score || (t.score == b.score && t.cand < b.cand)) b = t;
+    }
+    if (b.score == INT_MIN) return false;
+    const int side = b.cand & 1, rest = b.cand >> 1, d = rest / n, i = rest % n;
+    *out_dim = d;
+    *out_pos = side ? B.h_hi[(size_t)d * B.n_total + list[i]] + 2 * EPS
+                    : B.h_lo[(size_t)d * B.n_total + list[i]] - 2 * EPS;
+    return true;
+}
+
+/* kd_tree_split_node, kd-tree.c:315-419 */
+static int split_node(Builder &B, ndtabi_kd_node *node, const int *list, int n)
+{
+    ++B.total_nodes;
+    int split_dim = node->dim;
+    double split_pos = 0.0;
+    bool found;
+    if (n >= KD_GPU_MIN_ITEMS) { found = gpu_search(B, list, n, &split_dim, &split_pos); ++B.gpu_nodes; }
+    else { found = host_search(B, list, n, &split_dim, &split_pos); ++B.host_nodes; }
+    if (B.err) return -1;
+    if (!found) {   /* leaf, kd-tree.c:360-375 */
+        node->num = n;
+        node->dim = -1;
+        node->boundary = 0.0;
+        node->obj_ids = (int *)calloc((size_t)n, sizeof(int *));
+        node->objs = (void **)calloc((size_t)n, sizeof(void *));
+        for (int i = 0; i < n; ++i) {
+            node->obj_ids[i] = B.items[list[i]]->id;
+            node->objs[i] = B.items[list[i]]->obj_ptr;
+        }
+        node->left = node->right = NULL;
+        return 1;
+    }
+    node->dim = split_dim;
+    node->boundary = split_pos;
+    node->left = (ndtabi_kd_node *)calloc(1, sizeof(ndtabi_kd_node));
+    node->right = (ndtabi_kd_node *)calloc(1, sizeof(ndtabi_kd_node));
+    node->left->dim = node->right->dim = -1;                    /* kd_node_init */
+    int *l = (int *)malloc((size_t)(n ? n : 1) * sizeof(int)), *r = (int *)malloc((size_t)(n ? n : 1) * sizeof(int));
+    int nl = 0, nr = 0;
+    const double *lo = B.h_lo + (size_t)split_dim * B.n_total, *hi = B.h_hi + (size_t)split_dim * B.n_total;
+    for (int i = 0; i < n; ++i) {
+        const int it = list[i];
+        const double radius = ((ndtabi_object *)B.items[it]->obj_ptr)->bounds.radius;
+        if (radius < 0.0) continue;                               /* kd-tree.c:385-389 */
+        const double il = lo[it], iu = hi[it];
+        if (iu < split_pos - EPS) l[nl++] = it;
+        else if (il > split_pos + EPS) r[nr++] = it;
+        else { l[nl++] = it; r[nr++] = it; }
+    }
+    node->left->dim = (node->dim + 1) % B.dims;
+    node->right->dim = (node->dim + 1) % B.dims;
+    int rc = 0;
+    if (nl > 0 && nr > 0) {
+        if (split_node(B, node->left, l, nl) < 0) rc = -1;
+        if (rc == 0 && split_node(B, node->right, r, nr) < 0) rc = -1;
+    }
+    free(l); free(r);
+    return rc;
+}
+
+extern "C" int ndt_b200_kd_tree_build(void *tree_v, void *items_v)
+{
+    ndtabi_kd_tree *tree = (ndtabi_kd_tree *)tree_v;
+    kdb_item_list *items = (kdb_item_list *)items_v;
+    if (!tree || !items) return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_kd_tree_build: NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return ndt_set_error(NDT_B200_E_CUDA, "no CUDA device; libndt_b200 has no CPU path");
+    const int dims = tree->bb_lower.n, n = items->n;
+    if (dims < 1 || dims > NDT_MAX_DIM) return ndt_set_error(NDT_B200_E_ARG, "kd tree not initialised (kd_tree_init)");
+    if (tree->root == NULL) tree->root = (ndtabi_kd_node *)calloc(1, sizeof(ndtabi_kd_node));
+
+    /* kd-tree.c:428-459 */
+    int num_fin = 0, num_inf = 0;
+    for (int i = 0; i < n; ++i) {
+        if (((ndtabi_object *)items->items[i]->obj_ptr)->bounds.radius >= 0.0) ++num_fin; else ++num_inf;
+    }
+    tree->root->objs = (void **)calloc((size_t)num_fin, sizeof(void *));
+    tree->inf_obj_ptrs = (void **)calloc((size_t)num_inf, sizeof(void *));
+    tree->obj_num = 0;
+    tree->inf_obj_num = 0;
+    Builder B;
+    memset(&B, 0, sizeof B);
+    B.dims = dims; B.n_total = n; B.items = items->items;
+    B.h_lo = (double *)malloc((size_t)dims * (n ? n : 1) * sizeof(double));
+    B.h_hi = (double *)malloc((size_t)dims * (n ? n : 1) * sizeof(double));
+    int *root_list = (int *)malloc((size_t)(n ? n : 1) * sizeof(int));
+    int n_root = 0;
+    for (int i = 0; i < n; ++i) {
+        kdb_item *it = items->items[i];
+        it->id = i;
+        for (int d = 0; d < dims; ++d) { B.h_lo[(size_t)d * n + i] = it->lower.v[d]; B.h_hi[(size_t)d * n + i] = it->upper.v[d]; }
+        if (((ndtabi_object *)it->obj_ptr)->bounds.radius >= 0.0) {
+            tree->root->objs[tree->obj_num++] = it->obj_ptr;
+            root_list[n_root++] = i;
+            for (int d = 0; d < dims; ++d) {                     /* aabb_add, kd-tree.c:43-61 */
+                if (it->lower.v[d] < tree->bb_lower.v[d]) tree->bb_lower.v[d] = it->lower.v[d];
+                if (it->upper.v[d] > tree->bb_upper.v[d]) tree->bb_upper.v[d] = it->upper.v[d];
+            }
+        } else {
+            tree->inf_obj_ptrs[tree->inf_obj_num++] = it->obj_ptr;
+        }
+    }
+    tree->root->dim = 0;
+    tree->obj_num = n;                                            /* kd-tree.c:470 */
+
+    int rc = 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking);
+    const size_t vb = (size_t)dims * (n ? n : 1) * sizeof(double);
+    B.list_cap = (size_t)(n ? n : 1);
+    B.best_cap = (size_t)dims * ((2 * B.list_cap + KD_BLOCK - 1) / KD_BLOCK) + 8;
+    if (e == cudaSuccess) e = cudaMalloc(&B.d_lo, vb);
+    if (e == cudaSuccess) e = cudaMalloc(&B.d_hi, vb);
+    if (e == cudaSuccess) e = cudaMalloc(&B.d_list, B.list_cap * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&B.d_best, B.best_cap * sizeof(Best));
+    if (e == cudaSuccess) e = cudaMallocHost(&B.h_best, B.best_cap * sizeof(Best));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.d_lo, B.h_lo, vb, cudaMemcpyHostToDevice, B.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.d_hi, B.h_hi, vb, cudaMemcpyHostToDevice, B.st);
+    if (e != cudaSuccess) {
+        rc = ndt_set_error(NDT_B200_E_CUDA, "ndt_b200_kd_tree_build: %s", cudaGetErrorString(e));
+    } else {
+        rc = split_node(B, tree->root, root_list, n_root);
+        if (rc < 0) rc = ndt_set_error(NDT_B200_E_CUDA, "ndt_b200_kd_tree_build: %s", B.err ? B.err : "failed");
+    }
+    cudaFree(B.d_lo); cudaFree(B.d_hi); cudaFree(B.d_list); cudaFree(B.d_best);
+    if (B.h_best) cudaFreeHost(B.h_best);
+    if (B.st) cudaStreamDestroy(B.st);
+    free(B.h_lo); free(B.h_hi); free(root_list);
+    return rc;
+}

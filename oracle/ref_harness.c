@@ -290,8 +290,37 @@ int refh_trace_ray(const double *o, const double *v, double dist_limit,
     return r;
 }
 
+/* a second kd-tree over the SAME item list, built by an external builder with
+ * kd_tree_build's signature (used to check ndt_b200_kd_tree_build node for node) */
+static kd_tree_t g_alt;
+static int g_alt_open = 0;
+void *refh_items(void) { return &g_items; }
+void *refh_alt_tree_begin(void)
+{
+    if (g_alt_open) { hush(1); kd_tree_free(&g_alt); hush(0); }
+    kd_tree_init(&g_alt, g_scn.dimensions);
+    g_alt_open = 1;
+    return &g_alt;
+}
+void refh_alt_tree_end(void)
+{
+    if (g_alt_open) { hush(1); kd_tree_free(&g_alt); hush(0); g_alt_open = 0; }
+}
+/* the reference's own builder on the alternate tree, for timing */
+double refh_alt_tree_build_reference(void)
+{
+    struct timespec a, b;
+    hush(1);
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    kd_tree_build(&g_alt, &g_items);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    hush(0);
+    return (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+}
+
 int refh_end_frame(void)
 {
+    refh_alt_tree_end();
     if (!g_frame_open)
         return -1;
     hush(1);

@@ -54,6 +54,9 @@ class RefHarness:
         L.refh_ray_count.restype = C.c_long
         L.refh_ray_count.argtypes = [C.c_int]
         L.refh_set_specular.argtypes = [C.c_int]
+        L.refh_items.restype = C.c_void_p
+        L.refh_alt_tree_begin.restype = C.c_void_p
+        L.refh_alt_tree_build_reference.restype = C.c_double
         L.refh_init(os.path.join(REFDIR, "objects").encode())
         self.counting = key
         self._scene = None
@@ -104,6 +107,18 @@ class RefHarness:
     @property
     def get_bounds_ptr(self):
         return self.lib.refh_object_get_bounds_ptr()
+
+    @property
+    def items_ptr(self):
+        """&kditems of the open frame (kd_item_list_t*, ndt.c:1900)"""
+        return self.lib.refh_items()
+
+    def alt_tree_begin(self):
+        """a fresh kd_tree_init'ed kd_tree_t over the same items, for an external builder"""
+        return self.lib.refh_alt_tree_begin()
+
+    def alt_tree_end(self):
+        self.lib.refh_alt_tree_end()
 
     def num_items(self):
         return self.lib.refh_num_items()
