@@ -190,6 +190,26 @@ int refh_begin_frame(int dims, int frame, int frames, const char *cfg, double *k
     hush(0);
     g_frame_open = 1;
     g_dirx_scaled = 0;
+    save_dirx();
+    return 0;
+}
+
+/* render_image rescales cam.dirX in place on every call (ndt.c:926) and nothing
+ * else of the scene; restoring the aimed dirX lets a frame be rendered again
+ * (timing repeats) without rebuilding the scene and the kd-tree */
+static double g_dirx_saved[64];
+static void save_dirx(void)
+{
+    int k = g_scn.cam.dirX.n + (g_scn.cam.dirX.n & 1);
+    for (int i = 0; i < k && i < 64; ++i) g_dirx_saved[i] = g_scn.cam.dirX.v[i];
+}
+int refh_reaim(void)
+{
+    if (!g_frame_open)
+        return -1;
+    int k = g_scn.cam.dirX.n + (g_scn.cam.dirX.n & 1);
+    for (int i = 0; i < k && i < 64; ++i) g_scn.cam.dirX.v[i] = g_dirx_saved[i];
+    g_dirx_scaled = 0;
     return 0;
 }
 

@@ -96,6 +96,11 @@ class RefHarness:
     def end_frame(self):
         self.lib.refh_end_frame()
 
+    def reaim(self):
+        """restore the aimed camera basis, so render() can be repeated on the open frame"""
+        if self.lib.refh_reaim() != 0:
+            raise RuntimeError("refh_reaim: no open frame")
+
     @property
     def scene_ptr(self):
         return self.lib.refh_scene()
