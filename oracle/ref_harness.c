@@ -56,6 +56,7 @@ static scene_frames_fn g_frames = NULL;
 static scene_cleanup_fn g_cleanup = NULL;
 static object **g_flat = NULL;  /* kd item order: id -> object* */
 static int g_nflat = 0;
+static void save_dirx(void);
 
 /* ---- ray counter (used by the --wrap=trace_kd build only) -------------- */
 #define STRIPES 64
