@@ -12,6 +12,7 @@ device call raises NdtB200Error when the library or a CUDA device is missing.
 """
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -199,10 +200,9 @@ class Context:
         self.close()
 
     def __del__(self):
-        import sys
-        if sys is None or sys.is_finalizing():
-            return      # the CUDA runtime may already be gone at interpreter shutdown
         try:
+            if sys is None or sys.is_finalizing():
+                return  # the CUDA runtime may already be gone at interpreter shutdown
             self.close()
         except Exception:
             pass

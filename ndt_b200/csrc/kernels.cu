@@ -29,7 +29,9 @@
 
 using namespace ndt;
 
+#ifndef BLOCK
 #define BLOCK 128
+#endif
 #ifndef NDT_MIN_BLOCKS
 #define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
 #endif
@@ -317,6 +319,10 @@ struct ndt_b200_ctx {
 template <int NP, bool CNT> static int blocks_per_sm()
 {
     int b = 0;
+#ifndef NDT_NO_L1_CARVEOUT
+    /* the kernel uses no shared memory: give the whole 228 KB to L1 (scene data, kd stack, mailbox) */
+    cudaFuncSetAttribute(k_generation<NP, CNT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+#endif
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generation<NP, CNT>, BLOCK, 0) != cudaSuccess || b < 1) b = 1;
     return b;
 }
