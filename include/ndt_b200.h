@@ -132,6 +132,11 @@ int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_a
                           int aa_depth, int max_optic_depth, int specular,
                           void *img_copy, void *depth_copy);
 
+/* Page-locked host memory (cudaMallocHost) for render_tile outputs and flat
+ * scenes; plain malloc'ed buffers work too, only slower to copy. */
+void *ndt_b200_host_alloc(size_t bytes);
+void ndt_b200_host_free(void *p);
+
 /* Drop-in for kd_tree_build(kd_tree_t*, kd_item_list_t*) (kd-tree.c:421-477),
  * the serial pre-pass in front of the render path (ndt.c:1908; 10-13 s per
  * frame for BASELINE config 2).  Same arguments, same result: the reference's

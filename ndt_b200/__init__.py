@@ -91,6 +91,10 @@ def lib():
     L.ndt_b200_stream.argtypes = [C.c_void_p]
     L.ndt_b200_stream.restype = C.c_void_p
     L.ndt_b200_kd_tree_build.argtypes = [C.c_void_p, C.c_void_p]
+    L.ndt_b200_host_alloc.argtypes = [C.c_size_t]
+    L.ndt_b200_host_alloc.restype = C.c_void_p
+    L.ndt_b200_host_free.argtypes = [C.c_void_p]
+    L.ndt_b200_host_free.restype = None
     L.ndt_b200_trace_rays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     L.ndt_b200_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ndt_b200_render_image.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_HostApi), C.c_char_p, C.c_char_p,
@@ -164,13 +168,28 @@ def kd_tree_build(kd_tree_ptr, kd_item_list_ptr):
     return _check(lib().ndt_b200_kd_tree_build(kd_tree_ptr, kd_item_list_ptr))
 
 
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (ndt_b200_host_alloc); freed with the array."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = lib().ndt_b200_host_alloc(n)
+    if not p:
+        raise NdtB200Error(-3, lib().ndt_b200_last_error().decode(errors="replace"))
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib().ndt_b200_host_free, p)
+    return arr
+
+
 class Frame:
-    def __init__(self, tw, th, want):
-        self.rgba_f64 = np.empty((th, tw, 4), np.float64) if "f64" in want else None
-        self.rgba_u8 = np.empty((th, tw, 4), np.uint8) if "u8" in want else None
-        self.hit = np.empty((th, tw), np.uint8) if "hit" in want else None
-        self.obj_id = np.empty((th, tw), np.int32) if "id" in want else None
-        self.inv_depth = np.empty((th, tw), np.float64) if "depth" in want else None
+    def __init__(self, tw, th, want, pinned=False):
+        mk = pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dt))
+        self.rgba_f64 = mk((th, tw, 4), np.float64) if "f64" in want else None
+        self.rgba_u8 = mk((th, tw, 4), np.uint8) if "u8" in want else None
+        self.hit = mk((th, tw), np.uint8) if "hit" in want else None
+        self.obj_id = mk((th, tw), np.int32) if "id" in want else None
+        self.inv_depth = mk((th, tw), np.float64) if "depth" in want else None
         self.stats = None
 
 

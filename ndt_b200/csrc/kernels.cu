@@ -698,6 +698,20 @@ extern "C" int ndt_b200_trace_rays(ndt_b200_ctx *c, int n_rays, const double *or
     return 0;
 }
 
+/* page-locked host memory for the output buffers of ndt_b200_render_tile: the
+ * device->host copies then run at PCIe/NVLink-C2C speed instead of being
+ * staged through the driver's bounce buffer */
+extern "C" void *ndt_b200_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        ndt_set_error(NDT_B200_E_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+        return NULL;
+    }
+    return p;
+}
+extern "C" void ndt_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" int ndt_b200_fp64_peak(ndt_b200_ctx *c, int fused, double *gflops)
 {
     if (!c || !gflops) return ndt_set_error(NDT_B200_E_ARG, "NULL argument");
