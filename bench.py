@@ -169,7 +169,7 @@ def run_reference(args, rank, world):
     try:
         r = reference_sample(args.workload, args.steps, args.warmup)
     except Exception as e:  # the oracle always exists in a built tree; say why if not
-        print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+        emit({"impl": "reference", "unavailable": str(e)[:200]})
         return
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": r["mrays_unique"], "unit": "Mrays/s",
@@ -185,7 +185,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": r["mrays_unique"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -364,13 +364,26 @@ def run_ours(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints
+    (NCCL's version banner, the reference's printf chatter) was sent to stderr."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # fd 1 -> stderr for C libraries and print() alike
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
