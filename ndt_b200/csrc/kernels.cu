@@ -25,155 +25,30 @@
 #include <string.h>
 #include "ndt_abi.h"
 #include "ndt_internal.h"
-#include "wave.cuh"
+#include "gen.cuh"
 
-using namespace ndt;
-
-#ifndef BLOCK
-#define BLOCK 128
-#endif
-#ifndef NDT_MIN_BLOCKS
-#define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
-#endif
-/* experiments: -DNDT_ONLY_NP=8 instantiates a single dimension (fast builds) */
+/* per-NP launch tables (np_inst.cu); -DNDT_ONLY_NP=8 links a single dimension (fast experiment builds) */
 #ifdef NDT_ONLY_NP
-#define NDT_HAVE_NP(n) ((n) == NDT_ONLY_NP)
+#define NP_DECL(n)
+#define NP_REF(n) ((n) == NDT_ONLY_NP ? &NP_ONLY_SYM : NULL)
+#define CAT2(a, b) a##b
+#define CAT(a, b) CAT2(a, b)
+#define NP_ONLY_SYM CAT(ndt_np_ops_, NDT_ONLY_NP)
+extern const NpOps NP_ONLY_SYM;
 #else
-#define NDT_HAVE_NP(n) 1
+extern const NpOps ndt_np_ops_4, ndt_np_ops_6, ndt_np_ops_8, ndt_np_ops_10, ndt_np_ops_12;
+#define NP_REF(n) (&ndt_np_ops_##n)
 #endif
-
-struct GenArgs {
-    int gen;                 /* 0: rays are generated from pixels */
-    int start, count;        /* this generation's slots are [start, start+count) */
-    int n0;                  /* slots of generation 0 (tile padded to 8x4 blocks) */
-    int cap;                 /* record pool capacity */
-    int x0, y0, tw, th, bpr; /* tile, and 8-pixel blocks per tile row */
-    RayRec *rec;
-    void *rays;              /* RayIn<NP>[cap - n0], slot s lives at rays[s - n0] */
-    int *tail;               /* next free slot */
-    int *next;               /* work counter of this launch */
-    int *overflow;           /* [0] ray pool, [1] kd stack */
-    unsigned long long *stats; /* [0] shadow rays [1] flops [2] rays_ref [3] samples [4] hit pixels */
-    uint8_t *out_hit;
-    int32_t *out_id;
-    double *out_depth;
-    uint32_t *mb_bits;
-    uint32_t mb_stride, mb_words, mb_shift;
-};
-
-template <int NP, bool CNT>
-__global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scene sc, const GenArgs a)
+const NpOps *ndt_np_ops(int np)
 {
-    const int lane = threadIdx.x & 31;
-    Mailbox mb;
-    mb.bits = a.mb_bits; mb.stride = a.mb_stride;
-    mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
-    mb.words = a.mb_words; mb.group_shift = a.mb_shift;
-    mb.dirty = ~0ull;            /* first clear() wipes the whole column */
-    Tally<CNT> tally;
-    unsigned long long shadow_total = 0;
-    int kd_overflow = 0;
-    RayIn<NP> *rays = (RayIn<NP> *)a.rays;
-
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(a.next, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= a.count) break;
-        const int r = base + lane;
-        bool active = r < a.count;
-        double o[NP], v[NP], frac = 1.0;
-        int depth = sc.max_optic_depth;
-        int tx = 0, ty = 0;
-        if (a.gen == 0) {
-            const int blk = r >> 5;
-            tx = (blk % a.bpr) * 8 + (lane & 7);
-            ty = (blk / a.bpr) * 4 + (lane >> 3);
-            active = active && tx < a.tw && ty < a.th;
-            if (active) primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
-        } else if (active) {
-            const RayIn<NP> *in = rays + (a.start + r - a.n0);
-            NDT_UNROLL
-            for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
-            frac = in->frac;
-            depth = in->depth;
-        }
-
-        RayRec rec;
-        Spawn<NP> sp;
-        sp.want_refl = sp.want_refr = 0;
-        int p_hit = 0, p_id = -1;
-        double p_dist = -1.0;
-        uint32_t nsh = 0;
-        if (active) {
-            process_ray<NP, CNT>(sc, mb, o, v, frac, depth, rec, sp, p_hit, p_id, p_dist, nsh, kd_overflow, tally);
-            rec.nrays = 1u + nsh;
-            shadow_total += nsh;
-        }
-
-        /* hand out slots of the next generation: two ballots, one atomic per warp */
-        const bool q1 = active && sp.want_refl == 1;
-        const bool q2 = active && sp.want_refr == 1;
-        const unsigned b1 = __ballot_sync(0xffffffffu, q1);
-        const unsigned b2 = __ballot_sync(0xffffffffu, q2);
-        const int total = __popc(b1) + __popc(b2);
-        int wbase = 0;
-        if (total > 0) {
-            if (lane == 0) wbase = atomicAdd(a.tail, total);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        }
-        const bool fits = wbase + total <= a.cap;
-        if (total > 0 && !fits && lane == 0) atomicExch(a.overflow, 1);
-        const unsigned lt = (1u << lane) - 1u;
-        if (active) {
-            if (sp.want_refl == 2) rec.child_refl = CHILD_BLACK;
-            if (sp.want_refr == 2) rec.child_refr = CHILD_BLACK;
-            if (q1) {
-                const int s = wbase + __popc(b1 & lt);
-                rec.child_refl = fits ? s : CHILD_BLACK;
-                if (fits) {
-                    RayIn<NP> *out = rays + (s - a.n0);
-                    NDT_UNROLL
-                    for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refl_dir[i]; }
-                    out->frac = sp.refl_frac; out->depth = depth - 1; out->pad = 0;
-                }
-            }
-            if (q2) {
-                const int s = wbase + __popc(b1) + __popc(b2 & lt);
-                rec.child_refr = fits ? s : CHILD_BLACK;
-                if (fits) {
-                    RayIn<NP> *out = rays + (s - a.n0);
-                    NDT_UNROLL
-                    for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refr_dir[i]; }
-                    out->frac = sp.refr_frac; out->depth = depth - 1; out->pad = 0;
-                }
-            }
-            a.rec[a.start + r] = rec;
-            if (a.gen == 0) {
-                const size_t p = (size_t)ty * a.tw + tx;
-                if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
-                if (a.out_id) a.out_id[p] = p_id;
-                if (a.out_depth) a.out_depth[p] = (p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
-            }
-        } else if (a.gen == 0 && r < a.count) {
-            /* padding lane of a partial 8x4 block: keep the record defined */
-            RayRec z;
-            z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
-            z.h[0] = z.h[1] = z.h[2] = 0.0;
-            z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = 0;
-            a.rec[a.start + r] = z;
-        }
+    switch (np) {
+    case 4: return NP_REF(4);
+    case 6: return NP_REF(6);
+    case 8: return NP_REF(8);
+    case 10: return NP_REF(10);
+    case 12: return NP_REF(12);
     }
-
-    /* statistics: one atomic per warp */
-    for (int d = 16; d > 0; d >>= 1) shadow_total += __shfl_down_sync(0xffffffffu, shadow_total, d);
-    if (lane == 0 && shadow_total) atomicAdd(&a.stats[0], shadow_total);
-    if (CNT) {
-        unsigned long long f = tally.f;
-        for (int d = 16; d > 0; d >>= 1) f += __shfl_down_sync(0xffffffffu, f, d);
-        if (lane == 0 && f) atomicAdd(&a.stats[1], f);
-    }
-    if (kd_overflow) atomicExch(a.overflow + 1, 1);
+    return NULL;
 }
 
 __global__ void k_resolve(RayRec *rec, int start, int count, int specular)
@@ -228,41 +103,6 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
     }
 }
 
-/* trace_kd (object.c:683) for an explicit list of rays: the probe behind
- * ndt_b200_trace_rays, used by the per-primitive known-answer tests */
-template <int NP>
-__global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS)
-k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in, const double *limits,
-             int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
-             uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow)
-{
-    Mailbox mb;
-    mb.bits = mb_bits; mb.stride = mb_stride;
-    mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
-    mb.words = mb_words; mb.group_shift = mb_shift;
-    mb.dirty = ~0ull;
-    Tally<false> tally;
-    int ovf = 0;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += gridDim.x * blockDim.x) {
-        double o[NP], v[NP];
-        NDT_UNROLL
-        for (int i = 0; i < NP; ++i) {
-            o[i] = i < sc.n ? o_in[(size_t)r * sc.n + i] : 0.0;
-            v[i] = i < sc.n ? v_in[(size_t)r * sc.n + i] : 0.0;
-        }
-        Hit T;
-        trace_kd<NP, false>(sc, mb, o, v, limits ? limits[r] : -1.0, T, ovf, tally);
-        double p[NP], nr[NP];
-        vzero<NP>(p); vzero<NP>(nr);
-        if (T.id >= 0) materialise<NP>(sc, T.win, o, v, p, nr);
-        found[r] = T.found;
-        ids[r] = T.id;
-        ts[r] = T.t;
-        for (int i = 0; i < sc.n; ++i) { hits[(size_t)r * sc.n + i] = p[i]; normals[(size_t)r * sc.n + i] = nr[i]; }
-    }
-    if (ovf) atomicExch(overflow + 1, 1);
-}
-
 /* FP64 pipe probe: 8 independent chains per thread */
 template <bool FUSED> __global__ void k_fp64_probe(double *sink, int iters)
 {
@@ -298,6 +138,7 @@ struct ndt_b200_ctx {
     cudaEvent_t ev0, ev1;
     /* scene */
     char *d_blob; size_t blob_cap;
+    char *d_leafrec; size_t leafrec_cap;   /* LeafRec<npad>[n_leaf_refs] */
     ndt_flat_header hdr;
     Scene sc;
     int have_scene;
@@ -316,41 +157,14 @@ struct ndt_b200_ctx {
     int grid_blocks[2][8];               /* cached occupancy per (CNT, NP/2) */
 };
 
-template <int NP, bool CNT> static int blocks_per_sm()
-{
-    int b = 0;
-#ifndef NDT_NO_L1_CARVEOUT
-    /* the kernel uses no shared memory: give the whole 228 KB to L1 (scene data, kd stack, mailbox) */
-    cudaFuncSetAttribute(k_generation<NP, CNT>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-#endif
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generation<NP, CNT>, BLOCK, 0) != cudaSuccess || b < 1) b = 1;
-    return b;
-}
-
-template <int NP, bool CNT>
-static void launch_generation(int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
-{
-    k_generation<NP, CNT><<<blocks, BLOCK, 0, st>>>(sc, a);
-}
-
 static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
 {
     int &g = c->grid_blocks[cnt ? 1 : 0][np / 2];
     if (g == 0) {
-        int b = 1;
-#define OCC(N) case N: if (NDT_HAVE_NP(N)) b = cnt ? blocks_per_sm<N, true>() : blocks_per_sm<N, false>(); break
-        switch (np) { OCC(4); OCC(6); OCC(8); OCC(10); OCC(12); }
-#undef OCC
-        g = b * c->sm_count;
+        const NpOps *ops = ndt_np_ops(np);
+        g = (ops ? ops->blocks_per_sm(cnt) : 1) * c->sm_count;
     }
     return g;
-}
-
-static void dispatch_generation(int np, bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
-{
-#define GO(N) case N: if (NDT_HAVE_NP(N)) { if (cnt) launch_generation<N, true>(blocks, st, sc, a); else launch_generation<N, false>(blocks, st, sc, a); } break
-    switch (np) { GO(4); GO(6); GO(8); GO(10); GO(12); }
-#undef GO
 }
 
 static size_t rayin_bytes(int np) { return (size_t)(2 * np + 2) * sizeof(double); }
@@ -389,7 +203,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
+    cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
     cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out);
     cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -412,7 +226,7 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     const ndt_flat_header *h = &fs->h;
     int r = ndt_b200_flat_validate(fs, (size_t)h->total_bytes);
     if (r) return r;
-    if (h->npad < 4 || h->npad > 12)
+    if (h->npad < 4 || h->npad > 12 || !ndt_np_ops(h->npad))
         return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d dimensions: kernels are instantiated for 3..12", h->n);
     CK(cudaSetDevice(c->device));
     if (c->blob_cap < h->total_bytes) {
@@ -445,6 +259,21 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     s.focal_scale = h->focal_scale;
     if (h->tree_depth + 2 > KD_STACK)
         return ndt_set_error(NDT_B200_E_UNSUPPORTED, "kd-tree depth %d exceeds the traversal stack (%d)", h->tree_depth, KD_STACK);
+    /* the leaf-ordered record stream the warps stage through shared memory (warp.cuh) */
+    {
+        const size_t recb = (size_t)(h->npad + 2) * 8 + 16;
+        const size_t need = (size_t)(h->n_leaf_refs > 0 ? h->n_leaf_refs : 1) * recb;
+        if (c->leafrec_cap < need) {
+            CK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_leafrec); c->d_leafrec = NULL; c->leafrec_cap = 0;
+            CK(cudaMalloc(&c->d_leafrec, need + need / 4));
+            c->leafrec_cap = need + need / 4;
+        }
+        if (h->n_leaf_refs > 0) {
+            ndt_np_ops(h->npad)->pack_leaf(c->stream, s, h->n_leaf_refs, c->d_leafrec);
+            CK(cudaGetLastError());
+        }
+    }
     c->have_scene = 1;
     return 0;
 }
@@ -509,6 +338,7 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
     a.mb_words = (uint32_t)((h.n_items + 31) / 32); if (a.mb_words == 0) a.mb_words = 1;
     a.mb_shift = 0; while ((a.mb_words >> a.mb_shift) >= 64) ++a.mb_shift;
+    a.leafrec = c->d_leafrec;
 
     cudaStream_t st = c->stream;
     c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0;
@@ -527,11 +357,12 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
         if (ngen > 0) CK(cudaMemsetAsync(c->d_ctr + 1, 0, sizeof(int), st));
         int blocks = (count + BLOCK - 1) / BLOCK;
         if (blocks > full_grid) blocks = full_grid;
-        dispatch_generation(np, cnt, blocks, st, c->sc, a);
+        ndt_np_ops(np)->generation(cnt, blocks, st, c->sc, a);
         CK(cudaGetLastError());
         ++launches; ++ngen;
         CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (c->h_ctr[3] == 2) return ndt_set_error(NDT_B200_E_CUDA, "leaf staging copy timed out (mbarrier never completed)");
         if (c->h_ctr[3]) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
         if (c->h_ctr[2]) return ndt_set_error(NDT_B200_E_OVERFLOW, "ray pool exhausted (%zu records); render a smaller tile", c->rec_cap);
         int tail = c->h_ctr[0];
@@ -679,10 +510,9 @@ extern "C" int ndt_b200_trace_rays(ndt_b200_ctx *c, int n_rays, const double *or
     uint32_t words = (uint32_t)((h.n_items + 31) / 32); if (!words) words = 1;
     uint32_t shift = 0; while ((words >> shift) >= 64) ++shift;
     if (e == cudaSuccess) {
-#define TR(N) case N: if (NDT_HAVE_NP(N)) k_trace_rays<N><<<blocks, BLOCK, 0, st>>>(c->sc, n_rays, d_o, d_v, dist_limits ? d_lim : NULL, \
-        d_found, d_id, d_t, d_hit, d_nrm, c->d_mb, (uint32_t)(blocks * BLOCK), words, shift, c->d_ctr + 2); break
-        switch (np) { TR(4); TR(6); TR(8); TR(10); TR(12); }
-#undef TR
+        ndt_np_ops(np)->trace_rays(blocks, st, c->sc, n_rays, d_o, d_v, dist_limits ? d_lim : NULL, d_found, d_id, d_t,
+                                   d_hit, d_nrm, c->d_mb, (uint32_t)(blocks * BLOCK), words, shift, c->d_ctr + 2,
+                                   c->d_leafrec);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(found, d_found, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
@@ -694,6 +524,7 @@ extern "C" int ndt_b200_trace_rays(ndt_b200_ctx *c, int n_rays, const double *or
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     if (e != cudaSuccess) return ndt_set_error(NDT_B200_E_CUDA, "ndt_b200_trace_rays: %s", cudaGetErrorString(e));
+    if (c->h_ctr[3] == 2) return ndt_set_error(NDT_B200_E_CUDA, "leaf staging copy timed out (mbarrier never completed)");
     if (c->h_ctr[3]) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
     return 0;
 }

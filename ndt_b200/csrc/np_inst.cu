@@ -1,0 +1,48 @@
+/*
+ * np_inst.cu -- one padded dimension's kernels (gen.cuh); built once per NP with -DNDT_NP=N.
+ */
+#include "gen.cuh"
+
+#ifndef NDT_NP
+#error "build with -DNDT_NP=<4|6|8|10|12>"
+#endif
+#define CAT2(a, b) a##b
+#define CAT(a, b) CAT2(a, b)
+
+namespace {
+constexpr int NP = NDT_NP;
+
+template <bool CNT> size_t generation_smem() { return CNT ? 0 : (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(); }
+
+template <bool CNT> int occ()
+{
+    int b = 0;
+    const size_t sm = generation_smem<CNT>();
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k_generation<NP, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generation<NP, CNT>, BLOCK, sm) != cudaSuccess || b < 1) b = 1;
+    return b;
+}
+int blocks_per_sm(bool cnt) { return cnt ? occ<true>() : occ<false>(); }
+
+void generation(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
+{
+    if (cnt) k_generation<NP, true><<<blocks, BLOCK, generation_smem<true>(), st>>>(sc, a);
+    else k_generation<NP, false><<<blocks, BLOCK, generation_smem<false>(), st>>>(sc, a);
+}
+
+void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out)
+{
+    k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out);
+}
+
+void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const double *o, const double *v,
+                const double *limits, int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
+                uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
+                const void *leafrec)
+{
+    k_trace_rays<NP><<<blocks, BLOCK, (BLOCK / 32) * warp_smem_bytes<NP>(), st>>>(
+        sc, n_rays, o, v, limits, found, ids, ts, hits, normals, mb_bits, mb_stride, mb_words, mb_shift, overflow, leafrec);
+}
+}  // namespace
+
+extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { blocks_per_sm, generation, pack_leaf, trace_rays };

@@ -1,0 +1,440 @@
+/*
+ * warp.cuh -- the warp-synchronous form of the nearest-hit query (CUDA only).
+ *
+ * core.cuh's trace_kd walks one ray at a time: id -> bounding sphere ->
+ * object record -> geometry is a chain of dependent loads per object, and ncu
+ * showed the kernel latency bound on exactly that chain (profiles/r01_*).  Here
+ * the 32 rays of a warp walk the kd-tree on their own but visit LEAVES
+ * together:
+ *
+ *   1. every lane advances its traversal (kd-tree.c:482-568, same near/far rule
+ *      and deferred *t_ptr guards as trace_kd) until it stands on a leaf;
+ *   2. the warp picks the leaf of its lowest waiting lane; all lanes on that
+ *      leaf take part (8x4 pixel blocks: one leaf for the whole warp 9 times
+ *      out of 10), the others wait their turn;
+ *   3. the leaf's records stream through shared memory in chunks of 32: one
+ *      TMA bulk copy (cp.async.bulk + mbarrier) per chunk, double buffered, from
+ *      an array packed in leaf order at upload time (LeafRec: bounding sphere,
+ *      id, type, geometry offset = everything the loop needs before it touches
+ *      the geometry);
+ *   4. BROAD phase, no branches: each lane runs the ray-only part of the
+ *      bounding-sphere pre-test (bounding.c:52-84) on the 32 staged records
+ *      and keeps a 32-bit candidate mask;
+ *   5. NARROW phase over the union of the masks, in list order: mailbox,
+ *      the min_dist part of the pre-test (bounding.c:43-50), the per-type
+ *      intersection, trace()'s EPSILON hysteresis and early break
+ *      (object.c:692-747).
+ *
+ * Why this is the reference's result bit for bit.  trace() is sequential:
+ * min_dist, the mailbox and the break depend on everything before.  Only
+ * step 4 is hoisted out of that order, and it is a pure function of ray and
+ * sphere.  An object failing it is rejected by the reference at the same test
+ * whenever it gets there, in this leaf or any later one, so it never needs a
+ * mailbox bit; objects passing it are handled strictly in list order with the
+ * reference's own state.
+ */
+#pragma once
+#include "wave.cuh"
+
+namespace ndt {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CHUNK = 32;
+
+/* one leaf reference, packed at upload time (k_pack_leaf) */
+template <int NP> struct LeafRec {
+    double c[NP];         /* bounding sphere centre */
+    double r2, r;         /* radius^2, radius (<= 0: no pre-test, object.c:618) */
+    int32_t id;           /* kd item id = objects[] index */
+    uint32_t tfa;         /* type | flags << 8 | n_axes << 16 */
+    uint32_t geom_off;
+    int32_t report_id;
+};                        /* (NP + 2) * 8 + 16 bytes, a multiple of 16 */
+
+template <int NP> __host__ __device__ constexpr int warp_smem_bytes() { return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 16; }
+
+/* ---- mbarrier + TMA bulk copy (PTX ISA: cp.async.bulk, mbarrier) ------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+/* bounded wait: a wedged copy must surface as an error, never as a hung GPU */
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    for (int spin = 0; spin < (1 << 22); ++spin)
+        if (mbar_try_wait(bar, parity)) return true;
+    return false;
+}
+
+/* per-warp staging area and its pipeline state */
+template <int NP> struct WarpStage {
+    LeafRec<NP> *buf[2];
+    uint64_t *bar;        /* bar[0], bar[1] */
+    uint32_t phase;       /* bit s = parity the next wait on bar[s] uses */
+    const LeafRec<NP> *stream;
+    int lane;
+    int fault;            /* a bounded wait ran out */
+
+    __device__ __forceinline__ void init(unsigned char *smem, const void *leafrec, int lane_)
+    {
+        buf[0] = reinterpret_cast<LeafRec<NP> *>(smem);
+        buf[1] = buf[0] + CHUNK;
+        bar = reinterpret_cast<uint64_t *>(smem + 2 * CHUNK * sizeof(LeafRec<NP>));
+        phase = 0;
+        stream = static_cast<const LeafRec<NP> *>(leafrec);
+        lane = lane_;
+        fault = 0;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_init(bar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    /* lane 0 starts the copy of `cnt` records at stream[first] into buffer s */
+    __device__ __forceinline__ void fetch(int s, int first, int cnt)
+    {
+        if (lane == 0 && !fault) {
+            const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(LeafRec<NP>);
+            mbar_expect_tx(bar + s, bytes);
+            bulk_g2s(buf[s], stream + first, bytes, bar + s);
+        }
+    }
+    /* all 32 lanes wait on the same barrier, so `fault` stays warp-uniform; once set,
+     * nothing is fetched or waited for any more and the launch reports the error */
+    __device__ __forceinline__ void wait(int s)
+    {
+        if (fault) return;
+        if (!mbar_wait(bar + s, (phase >> s) & 1u)) fault = 1;
+        fault = __any_sync(FULL, fault) ? 1 : 0;
+        phase ^= 1u << s;
+    }
+};
+
+/* the ray-only half of bounding.c:34-85: desc = (v.oc)^2 - |oc|^2 + r^2 */
+template <int NP> __device__ __forceinline__ bool bsphere_ray_part(const double *c, double r2, const double *o, const double *v)
+{
+    double oc[NP];
+    vsub<NP>(o, c, oc);
+    double oc2 = vdot<NP>(oc, oc);
+    double voc = vdot<NP>(v, oc);
+    double voc2 = voc * voc;
+    double desc = voc2 - oc2 + r2;
+    return !(desc < 0.0 || (voc > 0.0 && voc2 > desc));
+}
+/* the min_dist half (bounding.c:43-50): true = rejected */
+template <int NP> __device__ __forceinline__ bool bsphere_far(const double *c, double r, const double *o, double min_dist)
+{
+    if (!(min_dist > 0)) return false;
+    double oc[NP];
+    vsub<NP>(o, c, oc);
+    double oc2 = vdot<NP>(oc, oc);
+    double mr = min_dist + r;
+    return oc2 > mr * mr;
+}
+
+template <int NP> __device__ __forceinline__ void lds_vec(double *d, const double *s)
+{
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) {
+        double2 t = *reinterpret_cast<const double2 *>(s + i);
+        d[i] = t.x; d[i + 1] = t.y;
+    }
+}
+
+/* trace() (object.c:692-747) of one leaf for the lanes with `mine`, all 32
+ * lanes of the warp taking part in the staging.  Per lane on return: min_dist
+ * (<0: nothing accepted), out_id, out_win. */
+template <int NP>
+__device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, int first, int count, bool mine,
+                                            Mailbox &mb, const double *o, const double *v, double dist_limit,
+                                            int &out_id, int &out_win)
+{
+    double min_dist = -1;
+    out_id = -1;
+    out_win = -1;
+    bool live = mine && !ws.fault;  /* false once this lane's trace() has hit its break */
+    if (ws.fault) return min_dist;
+    /* trace() hands one calloc'ed hit/normal pair to every object of the list (object.c:700-703):
+     * what vectNd_copy leaves in the pad lane carries over from one object to the next */
+    double res[NP], nrm[NP];
+    vzero<NP>(res);
+    vzero<NP>(nrm);
+    const int nch = (count + CHUNK - 1) / CHUNK;
+    int s = 0;
+    /* both buffers are free here: every warp_leaf drains what it started */
+    ws.fetch(0, first, count < CHUNK ? count : CHUNK);
+    for (int ch = 0; ch < nch; ++ch, s ^= 1) {
+        const int cnt = (count - ch * CHUNK) < CHUNK ? (count - ch * CHUNK) : CHUNK;
+        if (ch + 1 < nch) {
+            const int rest = count - (ch + 1) * CHUNK;
+            ws.fetch(s ^ 1, first + (ch + 1) * CHUNK, rest < CHUNK ? rest : CHUNK);
+        }
+        ws.wait(s);
+        const LeafRec<NP> *rec = ws.buf[s];
+
+        /* broad phase */
+        unsigned cand = 0;
+        if (live) {
+#pragma unroll 4
+            for (int k = 0; k < cnt; ++k) {
+                const double *rp = reinterpret_cast<const double *>(rec + k);
+                double c[NP];
+                lds_vec<NP>(c, rp);
+                const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);   /* r2, r */
+                const bool pass = !(rr.y > 0) || bsphere_ray_part<NP>(c, rr.x, o, v);
+                cand |= (pass ? 1u : 0u) << k;
+            }
+        }
+
+        /* narrow phase, list order, the warp in step on the union of the masks */
+        unsigned un = __reduce_or_sync(FULL, cand);
+        while (un) {
+            const int k = __ffs(un) - 1;
+            un &= un - 1;
+            if (live && ((cand >> k) & 1u)) {
+                const double *rp = reinterpret_cast<const double *>(rec + k);
+                const int4 meta = *reinterpret_cast<const int4 *>(rp + NP + 2);
+                const int id = meta.x;
+                bool skip = false;
+                {                                      /* object.c:706-713 */
+                    uint32_t *mword = mb.word((uint32_t)id >> 5);
+                    const uint32_t mcur = *mword, mbit = 1u << (id & 31);
+                    if (mcur & mbit) skip = true;
+                    else {
+                        *mword = mcur | mbit;
+                        mb.dirty |= 1ull << (((uint32_t)id >> 5) >> mb.group_shift);
+                    }
+                }
+                if (!skip) {
+                    const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);
+                    if (rr.y > 0) {
+                        double c[NP];
+                        lds_vec<NP>(c, rp);
+                        skip = bsphere_far<NP>(c, rr.y, o, min_dist);
+                    }
+                }
+                if (!skip) {
+                    ndt_flat_object fo;
+                    fo.type = (int32_t)((uint32_t)meta.y & 0xffu);
+                    fo.flags = (int32_t)(((uint32_t)meta.y >> 8) & 0xffu);
+                    fo.n_axes = (int32_t)((uint32_t)meta.y >> 16);
+                    fo.geom_off = (uint32_t)meta.z;
+                    fo.report_id = meta.w;
+                    Tally<false> none;
+                    bool ret;
+                    double dist = -1;
+                    int win = id;
+                    if (fo.type != NDT_T_HCUBE) {
+                        ret = intersect_prim<NP, false>(sc, fo, o, v, res, nrm, none);
+                        if (ret) dist = vdist<NP>(o, res);
+                    } else {
+                        /* nested trace() (hcube.c:236-250): no mailbox, no limit, own min_dist */
+                        const ndt_flat_object *top = sc.obj + id;
+                        int cid, cwin;
+                        const double in_min = trace_list<NP, false>(sc, (const int32_t *)nullptr, NDT_LDG(&top->child_count),
+                                                                    (Mailbox *)nullptr, o, v, -1.0, cid, cwin, none,
+                                                                    NDT_LDG(&top->child_begin));
+                        ret = !(in_min < 0);
+                        if (ret) { dist = in_min; win = cwin; }
+                    }
+                    if (ret) {
+                        if (dist > EPS && (dist + EPS < min_dist || min_dist < 0)) {
+                            min_dist = dist;
+                            out_id = fo.report_id;
+                            out_win = win;
+                        }
+                        if (dist_limit == 0.0 || dist < dist_limit) live = false;
+                    }
+                }
+            }
+        }
+        __syncwarp();           /* everyone is done with buf[s] before it is refilled */
+        if (ch + 1 < nch && !__ballot_sync(FULL, live)) {
+            ws.wait(s ^ 1);     /* drain the copy already in flight, then leave */
+            break;
+        }
+    }
+    return min_dist;
+}
+
+/* trace_kd (object.c:683) for the 32 rays of a warp.  Lanes with !want take
+ * part in the staging only.  Same contract as core.cuh's trace_kd. */
+template <int NP>
+__device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool want,
+                                              const double *o, const double *v, double dist_limit,
+                                              Hit &out, int &overflow, bool only_found)
+{
+    double o_dyn[NP], vinv[NP];
+    Tally<false> none;
+    double t = DBL_MAX, md = -1;
+    int ret = 0;
+    out.id = -1;
+    out.win = -1;
+    bool walking = false;
+    double tl = 0, tu = 0;
+    if (want) {
+        NDT_UNROLL
+        for (int i = 0; i < NP; ++i) {
+            double vi = v[i], r;
+            if (vi < EPS2 && vi >= 0.0) r = INV_EPS2;
+            else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
+            else r = 1.0 / vi;
+            vinv[i] = r;
+            o_dyn[i] = o[i];
+        }
+        /* infinite objects first, linear, no mailbox (kd-tree.c:592-594) */
+        md = trace_list<NP, false>(sc, sc.inf, sc.n_inf, (Mailbox *)nullptr, o, v, dist_limit, out.id, out.win, none);
+        ret = !(md < 0);
+        if (md > EPS) t = md;
+        if (!(only_found && ret) && sc.n_nodes > 0 && aabb_hit<NP>(sc, o, v, tl, tu)) {
+            mb.clear();
+            walking = true;
+        }
+    }
+
+    double lt = DBL_MAX;
+    int lret = 0, lid = -1, lwin = -1;
+    int s_node[KD_STACK];
+    double s_tl[KD_STACK], s_tu[KD_STACK], s_guard[KD_STACK];
+    int sp = 0, ni = 0, dim = -1;
+    bool have = true, after_leaf = false;
+
+    while (true) {
+        /* 1. advance to the next leaf (kd_node_intersect, kd-tree.c:482-568) */
+        int leaf_first = 0, leaf_count = 0, leaf_node = -1;
+        while (walking && leaf_node < 0) {
+            if (!after_leaf) {
+                if (!have) {
+                    if (sp == 0) { walking = false; break; }
+                    --sp;
+                    ni = s_node[sp]; tl = s_tl[sp]; tu = s_tu[sp];
+                    if (!(lt > s_guard[sp])) continue;
+                    have = true;
+                }
+                if (ni < 0 || tu < 0.0) { have = false; continue; }
+                const ndt_flat_node *nd = sc.nodes + ni;
+                dim = NDT_LDG(&nd->dim);
+                const int lcount = NDT_LDG(&nd->leaf_count);
+                after_leaf = true;
+                if (lcount > 0) {
+                    leaf_node = ni;
+                    leaf_first = NDT_LDG(&nd->leaf_begin);
+                    leaf_count = lcount;
+                }
+                continue;
+            }
+            after_leaf = false;
+            if (dim < 0) { have = false; continue; }
+            const ndt_flat_node *nd = sc.nodes + ni;
+            int nr = NDT_LDG(&nd->left), fr = NDT_LDG(&nd->right);
+            const double b = NDT_LDG(&nd->boundary);
+            const double vi = vinv[dim], oi = o_dyn[dim];
+            if (vi < EPS2) { int x = nr; nr = fr; fr = x; }
+            if (-INV_EPS2 <= vi && vi <= INV_EPS2) {
+                double tp = (b - oi) * vi;
+                if (tu < tp - EPS && lt > tl) {
+                    ni = nr;
+                } else if (tl > tp + EPS && lt > tl) {
+                    ni = fr;
+                } else {
+                    if (sp >= KD_STACK) { overflow = 1; have = false; continue; }
+                    s_node[sp] = fr; s_tl[sp] = tp - EPS; s_tu[sp] = tu; s_guard[sp] = tp; ++sp;
+                    if (lt > tl) { ni = nr; tu = tp + EPS; }
+                    else have = false;
+                }
+            } else {
+                bool go_near = (oi < b + EPS) && (lt > tl);
+                if (oi > b - EPS) {
+                    if (sp >= KD_STACK) { overflow = 1; have = false; continue; }
+                    s_node[sp] = fr; s_tl[sp] = tl; s_tu[sp] = tu; s_guard[sp] = tl; ++sp;
+                }
+                if (go_near) ni = nr;
+                else have = false;
+            }
+        }
+
+        /* 2. leaves, one distinct leaf at a time */
+        unsigned waiting = __ballot_sync(FULL, leaf_node >= 0);
+        if (!waiting) break;
+        while (waiting) {
+            const int src = __ffs(waiting) - 1;
+            const int L = __shfl_sync(FULL, leaf_node, src);
+            const int first = __shfl_sync(FULL, leaf_first, src);
+            const int count = __shfl_sync(FULL, leaf_count, src);
+            const bool mine = leaf_node == L;
+            waiting &= ~__ballot_sync(FULL, mine);
+            int oid, owin;
+            const double lmd = warp_leaf<NP>(sc, ws, first, count, mine, mb, o, v, dist_limit, oid, owin);
+            if (mine && !(lmd < 0)) {
+                lret = 1;
+                if (lmd < lt) {          /* trace sets t only when min_dist > EPS, which holds here */
+                    lt = lmd;
+                    lid = oid;
+                    lwin = owin;
+                }
+                /* the DIRECTIONAL shadow test consumes only the return value (ndt.c:241-249),
+                 * an OR over the leaves (kd-tree.c:594,607,616): final once one reports a hit */
+                if (only_found) walking = false;
+            }
+        }
+    }
+
+    if (lret) {
+        if (!ret || (lt > EPS && lt + EPS < t)) {   /* kd-tree.c:612-617 */
+            out.id = lid;
+            out.win = lwin;
+            ret |= lret;
+            md = lt;
+        }
+    }
+    out.found = ret;
+    out.t = md;
+}
+
+/* process_ray (wave.cuh) for a warp: every lane runs the same sequence of
+ * queries (the ray, then one per light), lanes without one idle through it */
+template <int NP>
+__device__ __forceinline__ void process_ray_warp(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool active,
+                                                 const double *src, const double *look, double frac, int depth,
+                                                 RayRec &rec, Spawn<NP> &sp, int &prim_hit, int &prim_id,
+                                                 double &prim_dist, uint32_t &n_shadow, int &overflow)
+{
+    Tally<false> none;
+    Shade<NP> S;
+    shade_init<NP>(S, rec, sp);
+    n_shadow = 0;
+    const int nl = sc.n_lights;
+    for (int it = -1; it < nl; ++it) {
+        const bool want = active && shade_setup<NP, false>(sc, S, it, src, look, n_shadow, none);
+        if (!__ballot_sync(FULL, want)) {
+            if (it < 0) break;      /* nobody traces the ray itself: nothing is shaded */
+            continue;
+        }
+        Hit T;
+        trace_kd_warp<NP>(sc, ws, mb, want, S.ro, S.rv, S.limit, T, overflow, S.ltype == NDT_L_DIRECTIONAL);
+        if (want) shade_after<NP, false>(sc, S, it, T, src, look, rec, prim_hit, prim_id, prim_dist, none);
+        if (it < 0 && !__ballot_sync(FULL, active && S.shaded)) break;
+    }
+    if (active) shade_finish<NP, false>(sc, S, look, frac, depth, rec, sp, none);
+}
+
+} /* namespace ndt */
