@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define NDT_FLAT_MAGIC   0x3146444eu /* "NDF1" */
-#define NDT_FLAT_VERSION 3u
+#define NDT_FLAT_VERSION 4u   /* 4: geometry blocks 16-byte aligned */
 #define NDT_MAX_DIM      16
 
 /* reference tolerances: vectNd.h:24-29, object.h:15-18 */
@@ -65,7 +65,9 @@ enum ndt_light_type { /* scene.h:17-23 */
 };
 
 /*
- * geom[] block layouts (all vectors npad doubles; A = n_axes):
+ * geom[] block layouts (all vectors npad doubles; A = n_axes).  Every block
+ * starts at an EVEN index of geom[] (16-byte aligned in the blob and in HBM) so
+ * that a block can be staged into shared memory with one TMA bulk copy:
  *  SPHERE    c, r^2                                         (sphere.c:18-32)
  *  HPLANE    p, n                                           (hplane.c:39-75)
  *  HDISK     p, n, r                                        (hdisk.c:15-34,61-85)

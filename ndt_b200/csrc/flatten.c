@@ -314,6 +314,9 @@ static int emit_object(fstate *st, ndtabi_object *o, int slot, int report_id)
     bs[np + 1] = o->bounds.radius * o->bounds.radius;
     fo->bs_radius = o->bounds.radius;
 
+    /* every geometry block starts 16-byte aligned (even double index): the device stages it
+     * into shared memory with one TMA bulk copy (cp.async.bulk needs 16-byte addresses) */
+    if (st->geom.n & 1) { double *pad; TAKE(pad, 1); pad[0] = 0.0; }
     size_t g0 = st->geom.n;
     NEED(g0 < 0xffffffffu, "geometry pool too large");
     fo->geom_off = (uint32_t)g0;
@@ -731,7 +734,7 @@ int ndt_b200_flat_validate(const void *blob, size_t bytes)
 #undef IN
     const ndt_flat_object *ob = NDT_FLAT_PTR(blob, const ndt_flat_object, h->off_objects);
     for (int i = 0; i < h->n_objects; ++i) {
-        if (ob[i].type < 0 || ob[i].type >= NDT_T_COUNT || ob[i].geom_off > h->n_geom ||
+        if (ob[i].type < 0 || ob[i].type >= NDT_T_COUNT || ob[i].geom_off > h->n_geom || (ob[i].geom_off & 1u) ||
             ob[i].report_id < 0 || ob[i].report_id >= h->n_items || ob[i].n_axes < 0 || ob[i].n_axes > h->n)
             return ndt_set_error(NDT_B200_E_ARG, "flat scene: object %d malformed", i);
         if (ob[i].type == NDT_T_HCUBE &&

@@ -53,7 +53,10 @@ __global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out)
     r.r = bs[NP];
     r.r2 = bs[NP + 1];
     r.id = id;
-    r.tfa = ((uint32_t)fo->type & 0xffu) | (((uint32_t)fo->flags & 0xffu) << 8) | ((uint32_t)fo->n_axes << 16);
+    int nd = geom_block_doubles(fo->type, fo->n_axes, NP);
+    /* ndt_b200_flat_validate guarantees geom_off even and n_axes <= n, so every block fits the staging buffer */
+    r.tfa = ((uint32_t)fo->type & 0xfu) | (((uint32_t)fo->flags & 0xfu) << 4) | (((uint32_t)fo->n_axes & 0xffu) << 8) |
+            ((uint32_t)((nd + 1) / 2) << 16);
     r.geom_off = fo->geom_off;
     r.report_id = fo->report_id;
     out[i] = r;

@@ -38,6 +38,13 @@
 
 namespace ndt {
 
+#ifndef NDT_BROAD_UNROLL
+#define NDT_BROAD_UNROLL 1    /* instruction-fetch bound: 1 measured faster than 2, 4, 8 */
+#endif
+#define NDT_STR2(x) #x
+#define NDT_STR(x) NDT_STR2(x)
+#define NDT_BROAD_LOOP _Pragma(NDT_STR(unroll NDT_BROAD_UNROLL))
+
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int CHUNK = 32;
 
@@ -46,12 +53,38 @@ template <int NP> struct LeafRec {
     double c[NP];         /* bounding sphere centre */
     double r2, r;         /* radius^2, radius (<= 0: no pre-test, object.c:618) */
     int32_t id;           /* kd item id = objects[] index */
-    uint32_t tfa;         /* type | flags << 8 | n_axes << 16 */
+    uint32_t tfa;         /* type | flags << 4 | n_axes << 8 | (16-byte units of the geometry block, 0 = not staged) << 16 */
     uint32_t geom_off;
     int32_t report_id;
 };                        /* (NP + 2) * 8 + 16 bytes, a multiple of 16 */
 
-template <int NP> __host__ __device__ constexpr int warp_smem_bytes() { return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 16; }
+/* doubles of the largest geometry block staged in shared memory (ndt_flat.h layouts):
+ * an orthotope / hcylinder with NP axes, or a facet */
+template <int NP> __host__ __device__ constexpr int geom_max_doubles()
+{
+    return (((NP + NP * NP + 3 * NP + 1) > (6 * NP + 8) ? (NP + NP * NP + 3 * NP + 1) : (6 * NP + 8)) + 1) & ~1;
+}
+/* doubles of an object's geometry block; 0 = nothing to stage (hcube) */
+__host__ __device__ inline int geom_block_doubles(int type, int m, int np)
+{
+    switch (type) {
+    case NDT_T_SPHERE: return np + 1;
+    case NDT_T_HPLANE: return 2 * np;
+    case NDT_T_HDISK: return 2 * np + 1;
+    case NDT_T_ORTHOTOPE: return np + m * np + 3 * m;
+    case NDT_T_FACET: return 6 * np + 7;
+    case NDT_T_HFACET: return 6 * np + 5;
+    case NDT_T_CYLINDER: return 2 * np + 4;
+    case NDT_T_HCYLINDER: return np + m * np + 3 * m + 1;
+    }
+    return 0;
+}
+
+/* per warp: two LeafRec chunks, two geometry blocks, four mbarriers */
+template <int NP> __host__ __device__ constexpr int warp_smem_bytes()
+{
+    return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 2 * geom_max_doubles<NP>() * 8 + 32;
+}
 
 /* ---- mbarrier + TMA bulk copy (PTX ISA: cp.async.bulk, mbarrier) ------------- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,7 +119,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
 /* per-warp staging area and its pipeline state */
 template <int NP> struct WarpStage {
     LeafRec<NP> *buf[2];
-    uint64_t *bar;        /* bar[0], bar[1] */
+    double *gbuf[2];      /* staged geometry blocks */
+    uint64_t *bar;        /* bar[0..1]: record chunks, bar[2..3]: geometry blocks */
     uint32_t phase;       /* bit s = parity the next wait on bar[s] uses */
     const LeafRec<NP> *stream;
     int lane;
@@ -96,7 +130,9 @@ template <int NP> struct WarpStage {
     {
         buf[0] = reinterpret_cast<LeafRec<NP> *>(smem);
         buf[1] = buf[0] + CHUNK;
-        bar = reinterpret_cast<uint64_t *>(smem + 2 * CHUNK * sizeof(LeafRec<NP>));
+        gbuf[0] = reinterpret_cast<double *>(smem + 2 * CHUNK * sizeof(LeafRec<NP>));
+        gbuf[1] = gbuf[0] + geom_max_doubles<NP>();
+        bar = reinterpret_cast<uint64_t *>(gbuf[1] + geom_max_doubles<NP>());
         phase = 0;
         stream = static_cast<const LeafRec<NP> *>(leafrec);
         lane = lane_;
@@ -104,6 +140,8 @@ template <int NP> struct WarpStage {
         if (lane == 0) {
             mbar_init(bar, 1);
             mbar_init(bar + 1, 1);
+            mbar_init(bar + 2, 1);
+            mbar_init(bar + 3, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -116,6 +154,14 @@ template <int NP> struct WarpStage {
             const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(LeafRec<NP>);
             mbar_expect_tx(bar + s, bytes);
             bulk_g2s(buf[s], stream + first, bytes, bar + s);
+        }
+    }
+    /* lane 0 starts the copy of a geometry block (n16 16-byte units at geom[off]) into gbuf[g] */
+    __device__ __forceinline__ void fetch_geom(int g, const double *geom, uint32_t off, uint32_t n16)
+    {
+        if (lane == 0 && !fault) {
+            mbar_expect_tx(bar + 2 + g, n16 * 16u);
+            bulk_g2s(gbuf[g], geom + off, n16 * 16u, bar + 2 + g);
         }
     }
     /* all 32 lanes wait on the same barrier, so `fault` stays warp-uniform; once set,
@@ -160,6 +206,37 @@ template <int NP> __device__ __forceinline__ void lds_vec(double *d, const doubl
     }
 }
 
+/* trace() for the lists that are not worth staging -- the infinite objects
+ * (kd-tree.c:592-594) and the faces nested in an hcube (hcube.c:236-250): one
+ * out-of-line copy of core.cuh's scalar loop, so that the hot leaf code above
+ * stays small in the instruction cache.  The ray is passed through local
+ * memory (copies, so that the caller's o/v stay in registers). */
+template <int NP>
+__device__ __noinline__ double trace_list_slow_impl(const Scene &sc, const int32_t *ids, int cnt, int base,
+                                                    const double *o_in, const double *v_in, double dist_limit,
+                                                    int *out_id, int *out_win)
+{
+    double o[NP], v[NP];
+    vcopy<NP>(o, o_in);
+    vcopy<NP>(v, v_in);
+    Tally<false> none;
+    int oid, owin;
+    const double md = trace_list<NP, false>(sc, ids, cnt, (Mailbox *)nullptr, o, v, dist_limit, oid, owin, none, base);
+    *out_id = oid;
+    *out_win = owin;
+    return md;
+}
+template <int NP>
+__device__ __forceinline__ double trace_list_slow(const Scene &sc, const int32_t *ids, int cnt, int base,
+                                                  const double *o, const double *v, double dist_limit,
+                                                  int *out_id, int *out_win)
+{
+    double ot[NP], vt[NP];
+    vcopy<NP>(ot, o);
+    vcopy<NP>(vt, v);
+    return trace_list_slow_impl<NP>(sc, ids, cnt, base, ot, vt, dist_limit, out_id, out_win);
+}
+
 /* trace() (object.c:692-747) of one leaf for the lanes with `mine`, all 32
  * lanes of the warp taking part in the staging.  Per lane on return: min_dist
  * (<0: nothing accepted), out_id, out_win. */
@@ -194,7 +271,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
         /* broad phase */
         unsigned cand = 0;
         if (live) {
-#pragma unroll 4
+            NDT_BROAD_LOOP
             for (int k = 0; k < cnt; ++k) {
                 const double *rp = reinterpret_cast<const double *>(rec + k);
                 double c[NP];
@@ -205,14 +282,28 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
             }
         }
 
-        /* narrow phase, list order, the warp in step on the union of the masks */
+        /* narrow phase, list order, the warp in step on the union of the masks; the geometry
+         * block of the next candidate is copied into shared memory while this one is tested */
         unsigned un = __reduce_or_sync(FULL, cand);
+        int gs = 0;
+        if (un) {
+            const int4 m0 = *reinterpret_cast<const int4 *>(reinterpret_cast<const double *>(rec + (__ffs(un) - 1)) + NP + 2);
+            if ((uint32_t)m0.y >> 16) ws.fetch_geom(0, sc.geom, (uint32_t)m0.z, (uint32_t)m0.y >> 16);
+        }
         while (un) {
             const int k = __ffs(un) - 1;
             un &= un - 1;
+            const unsigned alive = __ballot_sync(FULL, live);
+            if (!alive) un = 0;             /* every lane has left its trace(): stop after draining this copy */
+            if (un) {
+                const int4 m1 = *reinterpret_cast<const int4 *>(reinterpret_cast<const double *>(rec + (__ffs(un) - 1)) + NP + 2);
+                if ((uint32_t)m1.y >> 16) ws.fetch_geom(gs ^ 1, sc.geom, (uint32_t)m1.z, (uint32_t)m1.y >> 16);
+            }
+            const double *rp = reinterpret_cast<const double *>(rec + k);
+            const int4 meta = *reinterpret_cast<const int4 *>(rp + NP + 2);
+            const bool staged = ((uint32_t)meta.y >> 16) != 0;
+            if (staged) ws.wait(2 + gs);
             if (live && ((cand >> k) & 1u)) {
-                const double *rp = reinterpret_cast<const double *>(rec + k);
-                const int4 meta = *reinterpret_cast<const int4 *>(rp + NP + 2);
                 const int id = meta.x;
                 bool skip = false;
                 {                                      /* object.c:706-713 */
@@ -234,25 +325,26 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                 }
                 if (!skip) {
                     ndt_flat_object fo;
-                    fo.type = (int32_t)((uint32_t)meta.y & 0xffu);
-                    fo.flags = (int32_t)(((uint32_t)meta.y >> 8) & 0xffu);
-                    fo.n_axes = (int32_t)((uint32_t)meta.y >> 16);
+                    fo.type = (int32_t)((uint32_t)meta.y & 0xfu);
+                    fo.flags = (int32_t)(((uint32_t)meta.y >> 4) & 0xfu);
+                    fo.n_axes = (int32_t)(((uint32_t)meta.y >> 8) & 0xffu);
                     fo.geom_off = (uint32_t)meta.z;
                     fo.report_id = meta.w;
                     Tally<false> none;
                     bool ret;
                     double dist = -1;
                     int win = id;
-                    if (fo.type != NDT_T_HCUBE) {
-                        ret = intersect_prim<NP, false>(sc, fo, o, v, res, nrm, none);
+                    if (staged) {
+                        ret = intersect_prim<NP, false, LdShared>(sc, fo, ws.gbuf[gs], o, v, res, nrm, none);
                         if (ret) dist = vdist<NP>(o, res);
+                    } else if (fo.type != NDT_T_HCUBE) {
+                        ret = false;        /* unreachable: ndt_b200_upload refuses blocks that cannot be staged */
                     } else {
                         /* nested trace() (hcube.c:236-250): no mailbox, no limit, own min_dist */
                         const ndt_flat_object *top = sc.obj + id;
                         int cid, cwin;
-                        const double in_min = trace_list<NP, false>(sc, (const int32_t *)nullptr, NDT_LDG(&top->child_count),
-                                                                    (Mailbox *)nullptr, o, v, -1.0, cid, cwin, none,
-                                                                    NDT_LDG(&top->child_begin));
+                        const double in_min = trace_list_slow<NP>(sc, (const int32_t *)nullptr, NDT_LDG(&top->child_count),
+                                                                  NDT_LDG(&top->child_begin), o, v, -1.0, &cid, &cwin);
                         ret = !(in_min < 0);
                         if (ret) { dist = in_min; win = cwin; }
                     }
@@ -266,6 +358,8 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                     }
                 }
             }
+            __syncwarp();       /* gbuf[gs] is free again */
+            gs ^= 1;
         }
         __syncwarp();           /* everyone is done with buf[s] before it is refilled */
         if (ch + 1 < nch && !__ballot_sync(FULL, live)) {
@@ -283,8 +377,10 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
                                               const double *o, const double *v, double dist_limit,
                                               Hit &out, int &overflow, bool only_found)
 {
-    double o_dyn[NP], vinv[NP];
-    Tally<false> none;
+    /* per-axis values the walk indexes by the split dimension live in local memory; the loops
+     * that fill them stay rolled (one copy of the fp64 division sequence instead of NP or 2 NP:
+     * this per-ray prologue runs once per query and only costs instruction fetches) */
+    double o_dyn[NP], v_dyn[NP], vinv[NP];
     double t = DBL_MAX, md = -1;
     int ret = 0;
     out.id = -1;
@@ -293,21 +389,45 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
     double tl = 0, tu = 0;
     if (want) {
         NDT_UNROLL
+        for (int i = 0; i < NP; ++i) { o_dyn[i] = o[i]; v_dyn[i] = v[i]; }
+        NDT_NO_UNROLL
         for (int i = 0; i < NP; ++i) {
-            double vi = v[i], r;
+            double vi = v_dyn[i], r;
             if (vi < EPS2 && vi >= 0.0) r = INV_EPS2;
             else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
             else r = 1.0 / vi;
             vinv[i] = r;
-            o_dyn[i] = o[i];
         }
         /* infinite objects first, linear, no mailbox (kd-tree.c:592-594) */
-        md = trace_list<NP, false>(sc, sc.inf, sc.n_inf, (Mailbox *)nullptr, o, v, dist_limit, out.id, out.win, none);
+        md = trace_list_slow_impl<NP>(sc, sc.inf, sc.n_inf, 0, o_dyn, v_dyn, dist_limit, &out.id, &out.win);
         ret = !(md < 0);
         if (md > EPS) t = md;
-        if (!(only_found && ret) && sc.n_nodes > 0 && aabb_hit<NP>(sc, o, v, tl, tu)) {
-            mb.clear();
-            walking = true;
+        if (!(only_found && ret) && sc.n_nodes > 0) {
+            /* aabb_intersect, kd-tree.c:84-127 (aabb_hit of core.cuh, rolled) */
+            const double *lo = sc.aabb, *hi = sc.aabb + NP;
+            double l = -DBL_MAX, u = DBL_MAX;
+            bool behind = false;
+            NDT_NO_UNROLL
+            for (int i = 0; i < sc.n && !behind; ++i) {
+                const double vi = v_dyn[i], oi = o_dyn[i];
+                if (!(fabs(vi) < EPS2)) {
+                    double a = (NDT_LDG(lo + i) - oi) / vi;
+                    double b = (NDT_LDG(hi + i) - oi) / vi;
+                    if (a > b) { double x = a; a = b; b = x; }
+                    if (a > l) l = a;
+                    if (b < u) u = b;
+                    if (u < -EPS) behind = true;
+                }
+            }
+            if (!behind) {
+                l -= EPS;
+                u += EPS;
+                tl = l; tu = u;
+                if ((u >= -EPS) && (l <= u)) {
+                    mb.clear();
+                    walking = true;
+                }
+            }
         }
     }
 
