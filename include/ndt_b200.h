@@ -96,6 +96,7 @@ int ndt_b200_upload(ndt_b200_ctx *ctx, const ndt_flat_scene *fs);
 
 /* options: 0 = default */
 #define NDT_B200_OPT_COUNT_FLOPS 1u   /* run the instrumented kernels and fill stats.flops */
+#define NDT_B200_OPT_FUSED 2u         /* one fused kernel per bounce generation instead of the trace/shade wavefront (A/B measurements) */
 int ndt_b200_set_options(ndt_b200_ctx *ctx, uint32_t options);
 
 /* Render the tile [x0,x0+tw) x [y0,y0+th) of the uploaded frame into HOST

@@ -17,6 +17,9 @@ using namespace ndt;
 #ifndef NDT_MIN_BLOCKS
 #define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
 #endif
+#ifndef NDT_TRACE_MIN_BLOCKS
+#define NDT_TRACE_MIN_BLOCKS 4   /* measured: 4 beats 2, 3 and 5 on config 2 */
+#endif
 
 struct GenArgs {
     int gen;                 /* 0: rays are generated from pixels */
@@ -187,6 +190,265 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
     if (!CNT && ws.fault) atomicMax(a.overflow + 1, 2);
 }
 
+/* ---------------------------------------------------------------------------
+ * The wavefront: one bounce generation = four launches
+ *   k_trace (radiance rays)  nearest hit of every ray of the generation -> HitRec
+ *   k_shade<A>               per ray: hit point, normal, side tests (ndt.c:149-169);
+ *                            queues one shadow ray per light that needs one
+ *   k_trace (shadow rays)    -> HitRec per shadow ray
+ *   k_shade<B>               per ray: the light loop again, in the reference's order,
+ *                            now with the shadow answers; RayRec; reflection /
+ *                            refraction rays appended to the next generation
+ * k_trace holds nothing but the walk, the leaf loop and the primitives: measured on B200
+ * the fused kernel (k_generation) was bound by instruction fetch -- SM instruction cache
+ * 32 KB, hit rate 84 %, GPC instruction-cache requests at 73 % of peak -- because every ray
+ * dragged the shading code (acos / pow / sin / asin expansions, 60 KB) through the cache
+ * between two visits of the 20 KB leaf loop.  k_shade re-derives hit point and normal from
+ * the winner's identity (materialise) instead of carrying them through memory, and runs the
+ * light loop twice (A to emit the queries, B to consume the answers): both are a few hundred
+ * flops per ray against the thousands of a traversal.
+ * ------------------------------------------------------------------------- */
+struct HitRec {
+    double t;
+    int32_t id, win, found, pad;
+};                            /* 24 bytes */
+
+struct WaveArgs {
+    int gen;                 /* 0: rays are generated from pixels */
+    int start, count;        /* this generation's slots are [start, start+count) */
+    int n0;                  /* slots of generation 0 (tile padded to 8x4 blocks) */
+    int cap;                 /* record pool capacity */
+    int x0, y0, tw, th, bpr; /* tile, and 8-pixel blocks per tile row */
+    RayRec *rec;
+    void *rays;              /* RayIn<NP>[cap - n0], slot s lives at rays[s - n0] */
+    HitRec *hits;            /* [cap], by slot */
+    void *srays;             /* shadow queries RayIn<NP>[scap]: frac = dist_limit, depth = only-found flag */
+    HitRec *shits;           /* [scap] */
+    int *sslot;              /* [count * n_lights]: shadow slot of (ray, light) or -1 */
+    int scap;
+    int *ctr;                /* [0] tail [1] next (radiance) [2] pool overflow [3] kd overflow / staging fault
+                                [4] shadow tail [5] next (shadow) */
+    unsigned long long *stats; /* [0] shadow rays [1] flops [2] rays_ref [3] samples [4] hit pixels */
+    uint8_t *out_hit;
+    int32_t *out_id;
+    double *out_depth;
+    uint32_t *mb_bits;
+    uint32_t mb_stride, mb_words, mb_shift;
+    const void *leafrec;
+};
+
+/* the ray of slot r of this generation */
+template <int NP>
+__device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, int r, int lane, double *o, double *v,
+                                         double &frac, int &depth, int &tx, int &ty)
+{
+    bool active = r < a.count;
+    frac = 1.0;
+    depth = sc.max_optic_depth;
+    tx = ty = 0;
+    if (a.gen == 0) {
+        const int blk = r >> 5;
+        tx = (blk % a.bpr) * 8 + (lane & 7);
+        ty = (blk / a.bpr) * 4 + (lane >> 3);
+        active = active && tx < a.tw && ty < a.th;
+        if (active) primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
+    } else if (active) {
+        const RayIn<NP> *in = (const RayIn<NP> *)a.rays + (a.start + r - a.n0);
+        NDT_UNROLL
+        for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
+        frac = in->frac;
+        depth = in->depth;
+    }
+    return active;
+}
+
+/* MODE 0: the generation's own rays, MODE 1: its shadow queries */
+template <int NP, int MODE>
+__global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Scene sc, const WaveArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    Mailbox mb;
+    mb.bits = a.mb_bits; mb.stride = a.mb_stride;
+    mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
+    mb.words = a.mb_words; mb.group_shift = a.mb_shift;
+    mb.dirty = ~0ull;            /* first clear() wipes the whole column */
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WarpStage<NP> ws;
+    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(), a.leafrec, lane);
+    int kd_overflow = 0;
+    int count = a.count;
+    if (MODE == 1) {             /* written by k_shade<A>, complete before this launch started */
+        count = *(volatile const int *)(a.ctr + 4);
+        if (count > a.scap) count = a.scap;
+    }
+    int *next = a.ctr + (MODE ? 5 : 1);
+
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(next, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        const int r = base + lane;
+        double o[NP], v[NP], limit = -1.0;
+        bool want, only_found = false;
+        if (MODE == 0) {
+            double frac; int depth, tx, ty;
+            want = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
+        } else {
+            want = r < count;
+            if (want) {
+                const RayIn<NP> *in = (const RayIn<NP> *)a.srays + r;
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
+                limit = in->frac;
+                only_found = in->depth != 0;
+            }
+        }
+        Hit T;
+        trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, only_found);
+        if (ws.fault) break;     /* warp-uniform (warp.cuh) */
+        if (want) {
+            HitRec h;
+            h.t = T.t; h.id = T.id; h.win = T.win; h.found = T.found; h.pad = 0;
+            if (MODE == 0) a.hits[a.start + r] = h;
+            else a.shits[r] = h;
+        }
+    }
+    if (kd_overflow) atomicMax(a.ctr + 3, 1);
+    if (ws.fault) atomicMax(a.ctr + 3, 2);
+}
+
+/* PHASE 0 = A (emit the shadow queries), PHASE 1 = B (consume the answers, finish the ray) */
+template <int NP, int PHASE>
+__global__ void __launch_bounds__(BLOCK) k_shade(const Scene sc, const WaveArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;     /* the grid covers count rounded up to whole warps */
+    double o[NP], v[NP], frac;
+    int depth, tx, ty;
+    const bool active = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
+    Tally<false> none;
+    Shade<NP> S;
+    RayRec rec;
+    Spawn<NP> sp;
+    shade_init<NP>(S, rec, sp);
+    int p_hit = 0, p_id = -1;
+    double p_dist = -1.0;
+    uint32_t nsh = 0;
+    if (active) {
+        const HitRec h = a.hits[a.start + r];
+        Hit T;
+        T.t = h.t; T.id = h.id; T.win = h.win; T.found = h.found;
+        shade_setup<NP, false>(sc, S, -1, o, v, nsh, none);
+        shade_after<NP, false>(sc, S, -1, T, o, v, rec, p_hit, p_id, p_dist, none);
+    }
+    const int nl = sc.n_lights;
+    if (__ballot_sync(FULL, active && S.shaded)) {
+        for (int it = 0; it < nl; ++it) {
+            const bool want = active && shade_setup<NP, false>(sc, S, it, o, v, nsh, none);
+            if (PHASE == 0) {
+                /* slots of this light's queries: one ballot, one atomic per warp; queries of one
+                 * light from neighbouring pixels end up next to each other in the queue */
+                const unsigned b = __ballot_sync(FULL, want);
+                int wbase = 0;
+                if (b) {
+                    if (lane == 0) wbase = atomicAdd(a.ctr + 4, __popc(b));
+                    wbase = __shfl_sync(FULL, wbase, 0);
+                }
+                if (active) {
+                    int slot = -1;
+                    if (want) {
+                        slot = wbase + __popc(b & ((1u << lane) - 1u));
+                        if (slot < a.scap) {
+                            RayIn<NP> *out = (RayIn<NP> *)a.srays + slot;
+                            NDT_UNROLL
+                            for (int i = 0; i < NP; ++i) { out->o[i] = S.ro[i]; out->v[i] = S.rv[i]; }
+                            out->frac = S.limit;
+                            out->depth = S.ltype == NDT_L_DIRECTIONAL ? 1 : 0;
+                            out->pad = 0;
+                        } else {
+                            atomicExch(a.ctr + 2, 1);
+                            slot = -1;
+                        }
+                    }
+                    a.sslot[(size_t)r * nl + it] = slot;
+                }
+            } else if (want) {
+                const int slot = a.sslot[(size_t)r * nl + it];
+                Hit T;
+                T.t = -1; T.id = -1; T.win = -1; T.found = 0;
+                if (slot >= 0) {
+                    const HitRec h = a.shits[slot];
+                    T.t = h.t; T.id = h.id; T.win = h.win; T.found = h.found;
+                }
+                shade_after<NP, false>(sc, S, it, T, o, v, rec, p_hit, p_id, p_dist, none);
+            }
+        }
+    }
+    if (PHASE == 0) return;
+
+    if (active) {
+        shade_finish<NP, false>(sc, S, v, frac, depth, rec, sp, none);
+        rec.nrays = 1u + nsh;
+    }
+    /* hand out slots of the next generation: two ballots, one atomic per warp */
+    const bool q1 = active && sp.want_refl == 1;
+    const bool q2 = active && sp.want_refr == 1;
+    const unsigned b1 = __ballot_sync(FULL, q1);
+    const unsigned b2 = __ballot_sync(FULL, q2);
+    const int total = __popc(b1) + __popc(b2);
+    int wbase = 0;
+    if (total > 0) {
+        if (lane == 0) wbase = atomicAdd(a.ctr, total);
+        wbase = __shfl_sync(FULL, wbase, 0);
+    }
+    const bool fits = wbase + total <= a.cap;
+    if (total > 0 && !fits && lane == 0) atomicExch(a.ctr + 2, 1);
+    const unsigned lt = (1u << lane) - 1u;
+    RayIn<NP> *rays = (RayIn<NP> *)a.rays;
+    if (active) {
+        if (sp.want_refl == 2) rec.child_refl = CHILD_BLACK;
+        if (sp.want_refr == 2) rec.child_refr = CHILD_BLACK;
+        if (q1) {
+            const int s = wbase + __popc(b1 & lt);
+            rec.child_refl = fits ? s : CHILD_BLACK;
+            if (fits) {
+                RayIn<NP> *out = rays + (s - a.n0);
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refl_dir[i]; }
+                out->frac = sp.refl_frac; out->depth = depth - 1; out->pad = 0;
+            }
+        }
+        if (q2) {
+            const int s = wbase + __popc(b1) + __popc(b2 & lt);
+            rec.child_refr = fits ? s : CHILD_BLACK;
+            if (fits) {
+                RayIn<NP> *out = rays + (s - a.n0);
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refr_dir[i]; }
+                out->frac = sp.refr_frac; out->depth = depth - 1; out->pad = 0;
+            }
+        }
+        a.rec[a.start + r] = rec;
+        if (a.gen == 0) {
+            const size_t p = (size_t)ty * a.tw + tx;
+            if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
+            if (a.out_id) a.out_id[p] = p_id;
+            if (a.out_depth) a.out_depth[p] = (p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
+        }
+    } else if (a.gen == 0 && r < a.count) {
+        /* padding lane of a partial 8x4 block: keep the record defined */
+        RayRec z;
+        z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
+        z.h[0] = z.h[1] = z.h[2] = 0.0;
+        z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = 0;
+        a.rec[a.start + r] = z;
+    }
+    unsigned long long shadow_total = active ? nsh : 0;
+    for (int d = 16; d > 0; d >>= 1) shadow_total += __shfl_down_sync(FULL, shadow_total, d);
+    if (lane == 0 && shadow_total) atomicAdd(&a.stats[0], shadow_total);
+}
+
 /* trace_kd (object.c:683) for an explicit list of rays: the probe behind
  * ndt_b200_trace_rays, used by the per-primitive known-answer tests */
 template <int NP>
@@ -235,6 +497,9 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
 
 /* launchers of one NP, filled in by np_inst.cu */
 struct NpOps {
+    int (*trace_blocks_per_sm)(void);
+    void (*trace)(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
+    void (*shade)(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
     int (*blocks_per_sm)(bool cnt);
     void (*generation)(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a);
     void (*pack_leaf)(cudaStream_t st, const Scene &sc, int n_refs, void *out);

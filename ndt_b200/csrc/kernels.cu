@@ -146,7 +146,12 @@ struct ndt_b200_ctx {
     RayRec *d_rec; size_t rec_cap;       /* records */
     void *d_rays; size_t rays_bytes;
     uint32_t *d_mb; size_t mb_bytes;
-    int *d_ctr;                          /* [0] tail [1] next [2..3] overflow */
+    HitRec *d_hits; size_t hits_cap;     /* one per record slot */
+    char *d_srays; size_t srays_bytes;   /* shadow queries of one generation */
+    HitRec *d_shits; size_t shits_cap;
+    int *d_sslot; size_t sslot_cap;
+    int trace_grid[8];                   /* cached k_trace occupancy per NP/2 */
+    int *d_ctr;                          /* [0] tail [1] next [2..3] overflow [4] shadow tail [5] shadow next */
     unsigned long long *d_stats;         /* 8 counters */
     int *h_ctr; unsigned long long *h_stats; /* pinned mirrors */
     /* outputs for the host-buffer entry point */
@@ -155,6 +160,7 @@ struct ndt_b200_ctx {
     uint32_t options;
     ndt_b200_stats last;
     int grid_blocks[2][8];               /* cached occupancy per (CNT, NP/2) */
+    int light_type[256];                 /* host copy of lights[].type (which lights can ask a shadow query) */
 };
 
 static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
@@ -164,6 +170,23 @@ static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
         const NpOps *ops = ndt_np_ops(np);
         g = (ops ? ops->blocks_per_sm(cnt) : 1) * c->sm_count;
     }
+    return g;
+}
+
+static int grow(ndt_b200_ctx *c, void **p, size_t *cap, size_t want_bytes)
+{
+    if (*cap >= want_bytes) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(*p); *p = NULL; *cap = 0;
+    CK(cudaMalloc(p, want_bytes));
+    *cap = want_bytes;
+    return 0;
+}
+
+static int trace_grid_for(ndt_b200_ctx *c, int np)
+{
+    int &g = c->trace_grid[np / 2];
+    if (g == 0) g = ndt_np_ops(np)->trace_blocks_per_sm() * c->sm_count;
     return g;
 }
 
@@ -204,6 +227,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
+    cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_sslot);
     cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out);
     cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -257,6 +281,11 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     for (int k = 0; k < 4; ++k) s.bg[k] = h->bg[k];
     for (int k = 0; k < 3; ++k) s.ambient[k] = h->ambient[k];
     s.focal_scale = h->focal_scale;
+    if (h->n_lights > 256) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d lights (limit 256)", h->n_lights);
+    {
+        const ndt_flat_light *hl = (const ndt_flat_light *)((const char *)fs + h->off_lights);
+        for (int i = 0; i < h->n_lights; ++i) c->light_type[i] = hl[i].type;
+    }
     if (h->tree_depth + 2 > KD_STACK)
         return ndt_set_error(NDT_B200_E_UNSUPPORTED, "kd-tree depth %d exceeds the traversal stack (%d)", h->tree_depth, KD_STACK);
     /* the leaf-ordered record stream the warps stage through shared memory (warp.cuh) */
@@ -323,10 +352,81 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     const long long n0ll = (long long)bpr * bprows * 32;
     if (n0ll > 0x3fffffff) return ndt_set_error(NDT_B200_E_ARG, "tile too large; render in smaller tiles");
     const int n0 = (int)n0ll;
-    const int full_grid = grid_for(c, np, cnt);
+    const bool wave = !cnt && !(c->options & NDT_B200_OPT_FUSED);
+    const int full_grid = wave ? trace_grid_for(c, np) : grid_for(c, np, cnt);
     int r = ensure_pools(c, n0, np, full_grid * BLOCK);
     if (r) return r;
+    const uint32_t mb_words = (uint32_t)((h.n_items + 31) / 32) ? (uint32_t)((h.n_items + 31) / 32) : 1u;
+    uint32_t mb_shift = 0; while ((mb_words >> mb_shift) >= 64) ++mb_shift;
 
+    cudaStream_t st = c->stream;
+    c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0; c->h_ctr[4] = 0; c->h_ctr[5] = 0;
+    CK(cudaMemcpyAsync(c->d_ctr, c->h_ctr, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
+    CK(cudaEventRecord(c->ev0, st));
+
+    /* generation starts, for the backward fold */
+    int gstart[1024], gcount[1024], ngen = 0;
+    int start = 0, count = n0;
+    uint64_t launches = 0;
+    const NpOps *ops = ndt_np_ops(np);
+
+    if (wave) {
+        /* lights that can ask for a shadow query */
+        int n_sh = 0;
+        for (int i = 0; i < h.n_lights; ++i) n_sh += c->light_type[i] != NDT_L_AMBIENT;
+        if ((r = grow(c, (void **)&c->d_hits, &c->hits_cap, c->rec_cap * sizeof(HitRec)))) return r;
+        WaveArgs a;
+        memset(&a, 0, sizeof a);
+        a.n0 = n0; a.cap = (int)c->rec_cap;
+        a.x0 = x0; a.y0 = y0; a.tw = tw; a.th = th; a.bpr = bpr;
+        a.rec = c->d_rec; a.rays = c->d_rays; a.hits = c->d_hits;
+        a.ctr = c->d_ctr; a.stats = c->d_stats;
+        a.out_hit = (uint8_t *)d_hit; a.out_id = (int32_t *)d_obj_id; a.out_depth = (double *)d_inv_depth;
+        a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
+        a.mb_words = mb_words; a.mb_shift = mb_shift;
+        a.leafrec = c->d_leafrec;
+        while (count > 0) {
+            if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
+            gstart[ngen] = start; gcount[ngen] = count;
+            /* every ray of the generation may ask one shadow query per non-ambient light */
+            const size_t scap = (size_t)count * (size_t)(n_sh > 0 ? n_sh : 1);
+            if (scap > 0x7ffffff0u) return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow queue too large; render a smaller tile");
+            if ((r = grow(c, (void **)&c->d_srays, &c->srays_bytes, scap * rayin_bytes(np)))) return r;
+            if ((r = grow(c, (void **)&c->d_shits, &c->shits_cap, scap * sizeof(HitRec)))) return r;
+            if ((r = grow(c, (void **)&c->d_sslot, &c->sslot_cap, (size_t)count * (size_t)(h.n_lights > 0 ? h.n_lights : 1) * sizeof(int)))) return r;
+            a.srays = c->d_srays; a.shits = c->d_shits; a.sslot = c->d_sslot; a.scap = (int)scap;
+            a.gen = ngen; a.start = start; a.count = count;
+            if (ngen > 0) {      /* work counters and the shadow tail start from zero */
+                CK(cudaMemsetAsync(c->d_ctr + 1, 0, sizeof(int), st));
+                CK(cudaMemsetAsync(c->d_ctr + 4, 0, 2 * sizeof(int), st));
+            }
+            int tblocks = (count + BLOCK - 1) / BLOCK;
+            if (tblocks > full_grid) tblocks = full_grid;
+            const int sblocks = (count + BLOCK - 1) / BLOCK;
+            ops->trace(0, tblocks, st, c->sc, a);
+            ops->shade(0, sblocks, st, c->sc, a);
+            launches += 2;
+            if (n_sh > 0) {
+                /* the number of queries is only known on the device: a full persistent grid reads it there */
+                size_t want_blocks = (scap + BLOCK - 1) / BLOCK;
+                ops->trace(1, want_blocks < (size_t)full_grid ? (int)want_blocks : full_grid, st, c->sc, a);
+                ++launches;
+            }
+            ops->shade(1, sblocks, st, c->sc, a);
+            ++launches;
+            CK(cudaGetLastError());
+            ++ngen;
+            CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (c->h_ctr[3] == 2) return ndt_set_error(NDT_B200_E_CUDA, "leaf staging copy timed out (mbarrier never completed)");
+            if (c->h_ctr[3]) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
+            if (c->h_ctr[2]) return ndt_set_error(NDT_B200_E_OVERFLOW, "ray pool exhausted (%zu records); render a smaller tile", c->rec_cap);
+            int tail = c->h_ctr[0];
+            start += count;
+            count = tail - start;
+        }
+    } else {
     GenArgs a;
     memset(&a, 0, sizeof a);
     a.n0 = n0; a.cap = (int)c->rec_cap;
@@ -336,20 +436,8 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     a.stats = c->d_stats;
     a.out_hit = (uint8_t *)d_hit; a.out_id = (int32_t *)d_obj_id; a.out_depth = (double *)d_inv_depth;
     a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
-    a.mb_words = (uint32_t)((h.n_items + 31) / 32); if (a.mb_words == 0) a.mb_words = 1;
-    a.mb_shift = 0; while ((a.mb_words >> a.mb_shift) >= 64) ++a.mb_shift;
+    a.mb_words = mb_words; a.mb_shift = mb_shift;
     a.leafrec = c->d_leafrec;
-
-    cudaStream_t st = c->stream;
-    c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0;
-    CK(cudaMemcpyAsync(c->d_ctr, c->h_ctr, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
-    CK(cudaEventRecord(c->ev0, st));
-
-    /* generation starts, for the backward fold */
-    int gstart[1024], gcount[1024], ngen = 0;
-    int start = 0, count = n0;
-    uint64_t launches = 0;
     while (count > 0) {
         if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
         gstart[ngen] = start; gcount[ngen] = count;
@@ -357,7 +445,7 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
         if (ngen > 0) CK(cudaMemsetAsync(c->d_ctr + 1, 0, sizeof(int), st));
         int blocks = (count + BLOCK - 1) / BLOCK;
         if (blocks > full_grid) blocks = full_grid;
-        ndt_np_ops(np)->generation(cnt, blocks, st, c->sc, a);
+        ops->generation(cnt, blocks, st, c->sc, a);
         CK(cudaGetLastError());
         ++launches; ++ngen;
         CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -368,6 +456,7 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
         int tail = c->h_ctr[0];
         start += count;
         count = tail - start;
+    }
     }
     for (int g = ngen - 1; g >= 1; --g) {
         k_resolve<<<(gcount[g] + 255) / 256, 256, 0, st>>>(c->d_rec, gstart[g], gcount[g], h.specular);

@@ -30,6 +30,30 @@ void generation(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const Ge
     else k_generation<NP, false><<<blocks, BLOCK, generation_smem<false>(), st>>>(sc, a);
 }
 
+size_t trace_smem() { return (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(); }
+int trace_blocks_per_sm()
+{
+    int b0 = 0, b1 = 0;
+    const size_t sm = trace_smem();
+    if (sm > 48 * 1024) {
+        cudaFuncSetAttribute(k_trace<NP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(k_trace<NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_trace<NP, 0>, BLOCK, sm) != cudaSuccess || b0 < 1) b0 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<NP, 1>, BLOCK, sm) != cudaSuccess || b1 < 1) b1 = 1;
+    return b0 < b1 ? b0 : b1;
+}
+void trace(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
+{
+    if (mode) k_trace<NP, 1><<<blocks, BLOCK, trace_smem(), st>>>(sc, a);
+    else k_trace<NP, 0><<<blocks, BLOCK, trace_smem(), st>>>(sc, a);
+}
+void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
+{
+    if (phase) k_shade<NP, 1><<<blocks, BLOCK, 0, st>>>(sc, a);
+    else k_shade<NP, 0><<<blocks, BLOCK, 0, st>>>(sc, a);
+}
+
 void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out)
 {
     k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out);
@@ -45,4 +69,4 @@ void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const 
 }
 }  // namespace
 
-extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { blocks_per_sm, generation, pack_leaf, trace_rays };
+extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { trace_blocks_per_sm, trace, shade, blocks_per_sm, generation, pack_leaf, trace_rays };

@@ -12,6 +12,8 @@ key, W, H, *_ = bench.WORKLOADS[wl]
 flat = bench.load_flat(key, W, H)
 ctx = ndt_b200.Context(0)
 ctx.upload(flat)
+if os.environ.get('NDT_OPTS'):
+    ctx.set_options(int(os.environ['NDT_OPTS']))
 import torch
 out = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda:0")
 torch.cuda.synchronize()
@@ -21,5 +23,5 @@ for i in range(reps + 1):
     st = ctx.sync()
     if i:
         ms.append(st.device_ms)
-print(f"{os.environ.get('NDT_B200_LIB','default'):60s} {wl}: min {min(ms):8.3f} ms  median {np.median(ms):8.3f} ms  "
+print(f"{os.environ.get('NDT_B200_LIB','default')[-40:] + ' opts=' + os.environ.get('NDT_OPTS','0'):48s} {wl}: min {min(ms):8.3f} ms  median {np.median(ms):8.3f} ms  "
       f"rays {st.rays_unique}  gens {st.generations}  -> {st.rays_unique/min(ms)/1e3:.1f} Mrays/s", flush=True)
