@@ -17,6 +17,9 @@ using namespace ndt;
 #ifndef NDT_MIN_BLOCKS
 #define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
 #endif
+#ifndef NDT_SHADE_MIN_BLOCKS
+#define NDT_SHADE_MIN_BLOCKS 2
+#endif
 #ifndef NDT_TRACE_MIN_BLOCKS
 #define NDT_TRACE_MIN_BLOCKS 4   /* measured: 4 beats 2, 3 and 5 on config 2 */
 #endif
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
 
 /* PHASE 0 = A (emit the shadow queries), PHASE 1 = B (consume the answers, finish the ray) */
 template <int NP, int PHASE>
-__global__ void __launch_bounds__(BLOCK) k_shade(const Scene sc, const WaveArgs a)
+__global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(const Scene sc, const WaveArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;     /* the grid covers count rounded up to whole warps */

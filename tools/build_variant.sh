@@ -6,9 +6,10 @@ cd "$(dirname "$0")/../ndt_b200/csrc"
 mkdir -p build ../variants
 name=$1; shift
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -I../../include -I."
-nvcc $FL "$@" -DNDT_NP=8 -Xptxas -v -c np_inst.cu -o build/np8_$name.o 2> build/ptxas_$name.log &
-nvcc $FL "$@" -DNDT_ONLY_NP=8 -c kernels.cu -o build/kernels_$name.o &
+NPV=${NPV:-8}
+nvcc $FL "$@" -DNDT_NP=$NPV -Xptxas -v -c np_inst.cu -o build/np8_$name.o 2> build/ptxas_$name.log &
+nvcc $FL "$@" -DNDT_ONLY_NP=$NPV -c kernels.cu -o build/kernels_$name.o &
 wait
 [ -f build/flatten.o ] || make build/flatten.o build/error.o build/kdbuild.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libndt_b200_$name.so build/kernels_$name.o build/np8_$name.o build/kdbuild.o build/flatten.o build/error.o -lm -ldl
-grep -A2 "k_generationILi8ELb0" build/ptxas_$name.log | tr '\n' ' '; echo
+grep -A2 "k_shadeILi${NPV}ELi1\|k_traceILi${NPV}ELi0" build/ptxas_$name.log | tr '\n' ' '; echo
