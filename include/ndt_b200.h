@@ -50,6 +50,10 @@ typedef struct ndt_b200_ctx ndt_b200_ctx;
  * check use the very same centre/radius. */
 typedef struct ndt_b200_host_api {
     int (*object_get_bounds)(void *object);
+    /* vectNd_rotate2 (vectNd.c:271): only needed for VR / PANO cameras in a stereo mode, where
+     * get_pixel_color rotates the eye about the camera by each column's azimuth (ndt.c:519-525).
+     * May be NULL otherwise. */
+    int (*vectNd_rotate2)(void *v, void *center, void *v1, void *v2, double angle, void *res);
 } ndt_b200_host_api;
 
 /* What one render call did.  "rays" are nearest-hit queries, i.e. trace_kd
@@ -77,11 +81,17 @@ typedef struct ndt_b200_stats {
  * object.c:608-615), applies the dirX *= w/h scaling (ndt.c:926) to its own
  * copy and emits the flat scene.  `scene` is a `scene*`, `kdtree` a
  * `kd_tree_t*` of the reference.  Unknown object types, custom
- * get_color/get_reflect hooks, area lights and VR/PANO cameras are refused
- * with NDT_B200_E_UNSUPPORTED. */
+ * get_color/get_reflect hooks and area lights are refused with
+ * NDT_B200_E_UNSUPPORTED. */
 int ndt_b200_flatten(const void *scene, const void *kdtree, int width, int height,
                      int max_optic_depth, int specular,
                      const ndt_b200_host_api *host, ndt_flat_scene **out);
+/* Same for any stereo_mode of ndt.c:46-48 (MONO, SIDE_SIDE_3D, OVER_UNDER_3D, ANAGLYPH_3D,
+ * HIDEF_3D) and any camera type (NORMAL, VR, PANO: camera.c:504-556); ndt_b200_flatten is
+ * stereo_mode = MONO.  width x height is the OUTPUT frame (HIDEF_3D: height 2205). */
+int ndt_b200_flatten_view(const void *scene, const void *kdtree, int width, int height,
+                          int max_optic_depth, int specular, int stereo_mode,
+                          const ndt_b200_host_api *host, ndt_flat_scene **out);
 void ndt_b200_free_flat(ndt_flat_scene *fs);
 /* structural check of a blob received from disk or another rank */
 int ndt_b200_flat_validate(const void *blob, size_t bytes);
@@ -124,8 +134,8 @@ void *ndt_b200_stream(ndt_b200_ctx *ctx);
 /* Drop-in for render_image (ndt.c:900), same parameters and return value
  * (1).  `kdtree` is the extra argument: the reference reads its global
  * (ndt.c:68), a library cannot.  Supports what the device path supports:
- * samples == 1, stereo mode MONO, recursive_aa off; anything else returns a
- * negative status instead of rendering.  When img_copy is non-NULL it
+ * samples == 1, every stereo mode and camera type, recursive_aa off; anything
+ * else returns a negative status instead of rendering.  When img_copy is non-NULL it
  * receives the fp64 frame exactly like ndt.c:1024-1027. */
 int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_api *host,
                           char *name, char *depth_name, int width, int height,

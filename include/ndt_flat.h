@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define NDT_FLAT_MAGIC   0x3146444eu /* "NDF1" */
-#define NDT_FLAT_VERSION 4u   /* 4: geometry blocks 16-byte aligned */
+#define NDT_FLAT_VERSION 5u   /* 4: geometry blocks 16-byte aligned; 5: view tables (VR / PANO cameras, stereo modes) */
 #define NDT_MAX_DIM      16
 
 /* reference tolerances: vectNd.h:24-29, object.h:15-18 */
@@ -140,7 +140,27 @@ typedef struct ndt_flat_header {
     uint64_t off_leaf_refs;
     uint64_t off_inf;
     uint64_t off_lights;
+    /* -- version 5: cameras other than CAMERA_NORMAL and the stereo modes of render_pixel
+     *    (camera.c:504-556, ndt.c:578-653).  off_view == 0 means CAMERA_NORMAL + MONO: x and y
+     *    come from the pixel index (ndt.c:632-633).  Otherwise off_view points at doubles
+     *      ext[5*npad]        leftEye, rightEye, localX, localY, localZ (camera.h:60-75)
+     *      cols[width][4]     x, sin(x*hFov), cos(x*hFov), eye (0 centre 1 left 2 right)
+     *      rows[height][6]    y, sin(y*vFov), cos(y*vFov), y*y_size (PANO, camera.c:540),
+     *                         blank (HIDEF_3D rows 1080..1125, ndt.c:619-626), eye
+     *      eyes[width][2*npad] only if view_eyes: the eye rotated about cam.pos by the column's
+     *                         azimuth (VR / PANO stereo, ndt.c:519-525), left then right
+     *    All trigonometry is evaluated by the HOST's libm while flattening (W + H values), so the
+     *    device's primary rays are bit-identical to the reference's. */
+    int32_t cam_type;               /* camera.h:16-20: 0 CAMERA_NORMAL, 1 CAMERA_VR, 2 CAMERA_PANO */
+    int32_t stereo_mode;            /* ndt.c:46-48 */
+    int32_t view_eyes;              /* eyes[] present */
+    int32_t reserved2;
+    uint64_t off_view;
+    double cam_dist;                /* cam.focal_distance as passed to camera_target_point (ndt.c:515) */
 } ndt_flat_header;
+
+enum ndt_stereo_mode { NDT_MONO = 0, NDT_SIDE_SIDE_3D, NDT_OVER_UNDER_3D, NDT_ANAGLYPH_3D, NDT_HIDEF_3D };
+enum ndt_cam_type { NDT_CAM_NORMAL = 0, NDT_CAM_VR = 1, NDT_CAM_PANO = 2 };
 
 typedef struct ndt_flat_scene {     /* the blob starts with its header */
     ndt_flat_header h;

@@ -25,6 +25,7 @@
 extern char kdtree[];                    /* kd_tree_t kdtree, ndt.c:68 */
 extern int specular_enabled;             /* ndt.c:41 */
 int object_get_bounds(void *obj);        /* object.c:582 */
+int vectNd_rotate2(void *v, void *center, void *v1, void *v2, double angle, void *res);   /* vectNd.c:271 */
 int ndt_ref_main(int argc, char **argv); /* ndt.c:1390 compiled with -Dmain=ndt_ref_main */
 
 static unsigned char d2c(double d)       /* image.h:36-39 */
@@ -38,7 +39,7 @@ int render_image(void *scn, char *name, char *depth_name, int width, int height,
                  int mode, int threads, int aa_diff, int aa_depth, int max_optic_depth,
                  void *img_copy, void *depth_copy)
 {
-    ndt_b200_host_api host = { object_get_bounds };
+    ndt_b200_host_api host = { object_get_bounds, vectNd_rotate2 };
     ndtabi_image local;
     memset(&local, 0, sizeof local);
     ndtabi_image *img = img_copy ? (ndtabi_image *)img_copy : &local;

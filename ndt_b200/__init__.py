@@ -41,7 +41,11 @@ class Stats(C.Structure):
 
 
 class _HostApi(C.Structure):
-    _fields_ = [("object_get_bounds", C.c_void_p)]
+    _fields_ = [("object_get_bounds", C.c_void_p), ("vectNd_rotate2", C.c_void_p)]
+
+
+MONO, SIDE_SIDE_3D, OVER_UNDER_3D, ANAGLYPH_3D, HIDEF_3D = range(5)      # ndt.c:46-48
+CAMERA_NORMAL, CAMERA_VR, CAMERA_PANO = range(3)                          # camera.h:16-20
 
 
 class FlatHeader(C.Structure):
@@ -57,7 +61,9 @@ class FlatHeader(C.Structure):
                 ("off_camera", C.c_uint64), ("off_aabb", C.c_uint64), ("off_objects", C.c_uint64),
                 ("off_bspheres", C.c_uint64), ("off_geom", C.c_uint64), ("n_geom", C.c_uint64),
                 ("off_nodes", C.c_uint64), ("off_leaf_refs", C.c_uint64), ("off_inf", C.c_uint64),
-                ("off_lights", C.c_uint64)]
+                ("off_lights", C.c_uint64),
+                ("cam_type", C.c_int32), ("stereo_mode", C.c_int32), ("view_eyes", C.c_int32),
+                ("reserved2", C.c_int32), ("off_view", C.c_uint64), ("cam_dist", C.c_double)]
 
 
 _lib = None
@@ -76,6 +82,8 @@ def lib():
     L.ndt_b200_version.restype = C.c_char_p
     L.ndt_b200_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(_HostApi), C.POINTER(C.c_void_p)]
+    L.ndt_b200_flatten_view.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(_HostApi), C.POINTER(C.c_void_p)]
     L.ndt_b200_free_flat.argtypes = [C.c_void_p]
     L.ndt_b200_free_flat.restype = None
     L.ndt_b200_flat_validate.argtypes = [C.c_void_p, C.c_size_t]
@@ -139,6 +147,8 @@ class FlatScene:
         basis was scaled for width/height (ndt.c:926).  Only equal aspect ratios
         can be retargeted without re-flattening."""
         h = self.header
+        if h.off_view:
+            raise ValueError("view tables (VR / PANO / stereo) are per column and row; flatten the host scene again")
         if width * h.height != height * h.width:
             raise ValueError("aspect ratio differs; flatten the host scene again")
         hdr = FlatHeader.from_buffer_copy(self.blob[:C.sizeof(FlatHeader)])
@@ -149,13 +159,14 @@ class FlatScene:
         return len(self.blob)
 
 
-def flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth=128, specular=1, host_get_bounds=None):
-    """ndt_b200_flatten: host `scene*` + `kd_tree_t*` (ndt.c:68) -> FlatScene."""
+def flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth=128, specular=1, host_get_bounds=None,
+            stereo_mode=MONO, host_rotate2=None):
+    """ndt_b200_flatten_view: host `scene*` + `kd_tree_t*` (ndt.c:68) -> FlatScene."""
     L = lib()
-    host = _HostApi(host_get_bounds)
+    host = _HostApi(host_get_bounds, host_rotate2)
     out = C.c_void_p()
-    _check(L.ndt_b200_flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth, specular,
-                              C.byref(host), C.byref(out)))
+    _check(L.ndt_b200_flatten_view(scene_ptr, kdtree_ptr, width, height, max_optic_depth, specular, stereo_mode,
+                                   C.byref(host), C.byref(out)))
     try:
         total = C.c_uint64.from_address(out.value + 8).value
         return FlatScene(C.string_at(out.value, total))

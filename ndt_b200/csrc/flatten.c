@@ -530,6 +530,21 @@ int ndt_b200_flatten(const void *scene_v, const void *kdtree_v, int width, int h
                      int max_optic_depth, int specular,
                      const ndt_b200_host_api *host, ndt_flat_scene **out)
 {
+    return ndt_b200_flatten_view(scene_v, kdtree_v, width, height, max_optic_depth, specular, NDT_MONO, host, out);
+}
+
+/* temporary host vectNd (vectNd.h:42-51 layout) around a plain array, for calling vectNd_rotate2 */
+static void tmpvec_wrap(ndtabi_vec *v, double *store, int n)
+{
+    memset(v, 0, sizeof *v);
+    v->v = store;
+    v->n = n;
+}
+
+int ndt_b200_flatten_view(const void *scene_v, const void *kdtree_v, int width, int height,
+                          int max_optic_depth, int specular, int stereo_mode,
+                          const ndt_b200_host_api *host, ndt_flat_scene **out)
+{
     const ndtabi_scene *scn = scene_v;
     const ndtabi_kd_tree *kd = kdtree_v;
     fstate S, *st = &S;
@@ -549,8 +564,20 @@ int ndt_b200_flatten(const void *scene_v, const void *kdtree_v, int width, int h
     }
     const int n = st->n, np = st->np;
 
-    if (scn->cam.type != NDTABI_CAMERA_NORMAL) {
-        r = ndt_set_error(NDT_B200_E_UNSUPPORTED, "camera type %d: only CAMERA_NORMAL (camera.c:557-575) is on the device path", scn->cam.type);
+    if (scn->cam.type < 0 || scn->cam.type > 2) {
+        r = ndt_set_error(NDT_B200_E_UNSUPPORTED, "camera type %d (camera.h:16-20 knows NORMAL, VR, PANO)", scn->cam.type);
+        goto done;
+    }
+    if (stereo_mode < NDT_MONO || stereo_mode > NDT_HIDEF_3D) {
+        r = ndt_set_error(NDT_B200_E_UNSUPPORTED, "stereo mode %d (ndt.c:46-48)", stereo_mode);
+        goto done;
+    }
+    const int cam_type = scn->cam.type;
+    const int has_view = cam_type != NDT_CAM_NORMAL || stereo_mode != NDT_MONO;
+    /* VR / PANO in a stereo mode: the eye is rotated per column (ndt.c:519-525) */
+    const int view_eyes = cam_type != NDT_CAM_NORMAL && stereo_mode != NDT_MONO;
+    if (view_eyes && !(host && host->vectNd_rotate2)) {
+        r = ndt_set_error(NDT_B200_E_ARG, "VR / PANO camera in a stereo mode needs host->vectNd_rotate2 (vectNd.c:271)");
         goto done;
     }
 
@@ -653,6 +680,13 @@ int ndt_b200_flatten(const void *scene_v, const void *kdtree_v, int width, int h
     H.off_leaf_refs = off; off = align16(off + st->leaf.n * 4);
     H.off_inf = off;      off = align16(off + (size_t)kd->inf_obj_num * 4);
     H.off_lights = off;   off = align16(off + (size_t)n_l * sizeof(ndt_flat_light));
+    H.cam_type = cam_type; H.stereo_mode = stereo_mode; H.view_eyes = view_eyes;
+    H.cam_dist = scn->cam.focal_distance;
+    if (has_view) {
+        H.off_view = off;
+        off = align16(off + ((size_t)5 * np + (size_t)width * 4 + (size_t)height * 6 +
+                             (view_eyes ? (size_t)width * 2 * np : 0)) * 8);
+    }
     H.total_bytes = off;
 
     char *blob = NULL;
@@ -669,10 +703,73 @@ int ndt_b200_flatten(const void *scene_v, const void *kdtree_v, int width, int h
             r = ndt_set_error(NDT_B200_E_ARG, "camera vectors not aimed (camera_aim must run first, ndt.c:1925)");
             goto done;
         }
-        v_scale(dx, width / (double)height, dx, np);   /* ndt.c:926 */
+        if (stereo_mode != NDT_HIDEF_3D) v_scale(dx, width / (double)height, dx, np);   /* ndt.c:925-929 */
+        else v_scale(dx, width / (double)1080, dx, np);
         double sd = v_dist(orig, pos, np);             /* camera.c:567 */
         H.use_focal = sd > EPS;
         H.focal_scale = H.use_focal ? scn->cam.focal_distance / sd : 0.0;
+    }
+    if (has_view) {
+        /* render_pixel (ndt.c:578-653) per column / row, camera_target_point's trigonometry
+         * (camera.c:507-556) and the per-column eye of VR stereo (ndt.c:519-525), evaluated here
+         * with the host's libm so that the device reproduces the reference's primary rays exactly */
+        double *ext = (double *)(blob + H.off_view);
+        double *cols = ext + 5 * (size_t)np, *rows = cols + (size_t)width * 4, *eyes = rows + (size_t)height * 6;
+        const ndtabi_camera *cam = &scn->cam;
+        if (load_vec(st, &cam->leftEye, ext) || load_vec(st, &cam->rightEye, ext + np) ||
+            load_vec(st, &cam->localX, ext + 2 * np) || load_vec(st, &cam->localY, ext + 3 * np) ||
+            load_vec(st, &cam->localZ, ext + 4 * np)) {
+            free(blob); free(fl);
+            r = ndt_set_error(NDT_B200_E_ARG, "camera eyes / local axes not aimed (camera_aim must run first)");
+            goto done;
+        }
+        const double x_scale = stereo_mode == NDT_SIDE_SIDE_3D ? 0.5 : 1.0;
+        const double y_scale = stereo_mode == NDT_OVER_UNDER_3D ? 0.5 : 1.0;
+        const double dist = cam->focal_distance;
+        for (int i = 0; i < width; ++i) {
+            double ip = i;
+            int eye = 0;
+            if (stereo_mode == NDT_SIDE_SIDE_3D) {
+                if (i < width / 2) { ip = ip / x_scale; eye = 1; }
+                else { ip = (ip - width / 2) / x_scale; eye = 2; }
+            }
+            const double x = ip / (double)width - 0.5;
+            const double azi = x * cam->hFov;
+            double *c = cols + (size_t)i * 4;
+            c[0] = x; c[1] = sin(azi); c[2] = cos(azi); c[3] = eye;
+            if (view_eyes) {
+                for (int e = 0; e < 2; ++e) {
+                    double tmp[NDT_MAX_DIM] __attribute__((aligned(16))) = {0};
+                    ndtabi_vec vv;
+                    double *dst = eyes + ((size_t)i * 2 + e) * np;
+                    memcpy(tmp, ext + (size_t)e * np, (size_t)np * 8);
+                    tmpvec_wrap(&vv, tmp, n);
+                    host->vectNd_rotate2(&vv, (void *)&cam->pos, (void *)&cam->localX, (void *)&cam->localZ, azi, &vv);
+                    memcpy(dst, tmp, (size_t)np * 8);
+                }
+            }
+        }
+        const double y_size = 2.0 * tan(cam->vFov / 2.0) * dist;      /* camera.c:540 */
+        for (int j = 0; j < height; ++j) {
+            double jp = j;
+            int eye = 0, blank = 0;
+            if (stereo_mode == NDT_OVER_UNDER_3D) {
+                if (j < height / 2) { jp = jp / y_scale; eye = 1; }
+                else { jp = (jp - height / 2) / y_scale; eye = 2; }
+            }
+            double y;
+            if (stereo_mode == NDT_HIDEF_3D) {
+                if (j < 1080) eye = 1;
+                else if (j > (1080 + 45)) { jp = j - (1080 + 45); eye = 2; }
+                else blank = 1;
+                y = -(jp / 1080.0 - 0.5);
+            } else {
+                y = -(jp / (double)height - 0.5);
+            }
+            const double alt = y * cam->vFov;
+            double *rr = rows + (size_t)j * 6;
+            rr[0] = y; rr[1] = sin(alt); rr[2] = cos(alt); rr[3] = y * y_size; rr[4] = blank; rr[5] = eye;
+        }
     }
     {
         double *bb = (double *)(blob + H.off_aabb);
@@ -729,8 +826,13 @@ int ndt_b200_flat_validate(const void *blob, size_t bytes)
         !IN(h->off_nodes, (size_t)h->n_nodes * sizeof(ndt_flat_node)) ||
         !IN(h->off_leaf_refs, (size_t)h->n_leaf_refs * 4) ||
         !IN(h->off_inf, (size_t)h->n_inf * 4) ||
-        !IN(h->off_lights, (size_t)h->n_lights * sizeof(ndt_flat_light)))
+        !IN(h->off_lights, (size_t)h->n_lights * sizeof(ndt_flat_light)) ||
+        (h->off_view && !IN(h->off_view, ((size_t)5 * h->npad + (size_t)h->width * 4 + (size_t)h->height * 6 +
+                                          (h->view_eyes ? (size_t)h->width * 2 * h->npad : 0)) * 8)))
         return ndt_set_error(NDT_B200_E_ARG, "flat scene: array outside the blob");
+    if (h->cam_type < 0 || h->cam_type > 2 || h->stereo_mode < 0 || h->stereo_mode > NDT_HIDEF_3D ||
+        ((h->cam_type != NDT_CAM_NORMAL || h->stereo_mode != NDT_MONO) && !h->off_view))
+        return ndt_set_error(NDT_B200_E_ARG, "flat scene: camera type / stereo mode without view tables");
 #undef IN
     const ndt_flat_object *ob = NDT_FLAT_PTR(blob, const ndt_flat_object, h->off_objects);
     for (int i = 0; i < h->n_objects; ++i) {

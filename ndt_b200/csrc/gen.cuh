@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
             tx = (blk % a.bpr) * 8 + (lane & 7);
             ty = (blk / a.bpr) * 4 + (lane >> 3);
             active = active && tx < a.tw && ty < a.th;
-            if (active) primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
+            if (active) active = primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
         } else if (active) {
             const RayIn<NP> *in = rays + (a.start + r - a.n0);
             NDT_UNROLL
@@ -176,8 +176,14 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
             RayRec z;
             z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
             z.h[0] = z.h[1] = z.h[2] = 0.0;
-            z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = 0;
+            z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
             a.rec[a.start + r] = z;
+            if (tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
+                const size_t p = (size_t)ty * a.tw + tx;
+                if (a.out_hit) a.out_hit[p] = 0;
+                if (a.out_id) a.out_id[p] = -1;
+                if (a.out_depth) a.out_depth[p] = 0.0;
+            }
         }
     }
 
@@ -254,7 +260,7 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, int
         tx = (blk % a.bpr) * 8 + (lane & 7);
         ty = (blk / a.bpr) * 4 + (lane >> 3);
         active = active && tx < a.tw && ty < a.th;
-        if (active) primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
+        if (active) active = primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
     } else if (active) {
         const RayIn<NP> *in = (const RayIn<NP> *)a.rays + (a.start + r - a.n0);
         NDT_UNROLL
@@ -444,8 +450,14 @@ __global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(const Sce
         RayRec z;
         z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
         z.h[0] = z.h[1] = z.h[2] = 0.0;
-        z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = 0;
+        z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
         a.rec[a.start + r] = z;
+        if (tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
+            const size_t p = (size_t)ty * a.tw + tx;
+            if (a.out_hit) a.out_hit[p] = 0;
+            if (a.out_id) a.out_id[p] = -1;
+            if (a.out_depth) a.out_depth[p] = 0.0;
+        }
     }
     unsigned long long shadow_total = active ? nsh : 0;
     for (int d = 16; d > 0; d >>= 1) shadow_total += __shfl_down_sync(FULL, shadow_total, d);

@@ -68,7 +68,7 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
                          double *out_f64, uint8_t *out_u8, unsigned long long *stats)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long rays_ref = 0, samples = 0, hits = 0;
+    unsigned long long rays_ref = 0, samples = 0, hits = 0, traced = 0;
     if (p < tw * th) {
         const int tx = p % tw, ty = p / tw;
         const int slot = ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7);
@@ -76,8 +76,9 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
         const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
         const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
         resolve_rec(r, c1, c2, specular);
-        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4];
-        const int ns = replay_samples(l, o);
+        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4] = { 0.0, 0.0, 0.0, 0.0 };
+        /* a pixel render_pixel leaves black without calling get_pixel_color has no sample loop */
+        const int ns = (r.flags & REC_UNTRACED) ? 0 : replay_samples(l, o);
         if (out_f64) {
             double2 *d = reinterpret_cast<double2 *>(out_f64 + 4 * (size_t)p);
             d[0] = make_double2(o[0], o[1]);
@@ -90,16 +91,19 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
         rays_ref = (unsigned long long)r.nrays * (unsigned long long)ns;
         samples = (unsigned long long)ns;
         hits = r.flags & 1u;
+        traced = (r.flags & REC_UNTRACED) ? 0 : 1;
     }
     for (int d = 16; d > 0; d >>= 1) {
         rays_ref += __shfl_down_sync(0xffffffffu, rays_ref, d);
         samples += __shfl_down_sync(0xffffffffu, samples, d);
         hits += __shfl_down_sync(0xffffffffu, hits, d);
+        traced += __shfl_down_sync(0xffffffffu, traced, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (rays_ref) atomicAdd(&stats[2], rays_ref);
         if (samples) atomicAdd(&stats[3], samples);
         if (hits) atomicAdd(&stats[4], hits);
+        if (traced) atomicAdd(&stats[5], traced);
     }
 }
 
@@ -151,6 +155,7 @@ struct ndt_b200_ctx {
     HitRec *d_shits; size_t shits_cap;
     int *d_sslot; size_t sslot_cap;
     int trace_grid[8];                   /* cached k_trace occupancy per NP/2 */
+    char *d_ana; size_t ana_bytes;       /* ANAGLYPH_3D: the two eyes' fp64 frames */
     int *d_ctr;                          /* [0] tail [1] next [2..3] overflow [4] shadow tail [5] shadow next */
     unsigned long long *d_stats;         /* 8 counters */
     int *h_ctr; unsigned long long *h_stats; /* pinned mirrors */
@@ -227,7 +232,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
-    cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_sslot);
+    cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_sslot);
     cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out);
     cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -281,6 +286,9 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     for (int k = 0; k < 4; ++k) s.bg[k] = h->bg[k];
     for (int k = 0; k < 3; ++k) s.ambient[k] = h->ambient[k];
     s.focal_scale = h->focal_scale;
+    s.view = h->off_view ? (const double *)(b + h->off_view) : NULL;
+    s.cam_type = h->cam_type; s.stereo_mode = h->stereo_mode; s.view_eyes = h->view_eyes;
+    s.eye_override = 0; s.cam_dist = h->cam_dist;
     if (h->n_lights > 256) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d lights (limit 256)", h->n_lights);
     {
         const ndt_flat_light *hl = (const ndt_flat_light *)((const char *)fs + h->off_lights);
@@ -336,11 +344,62 @@ static int ensure_pools(ndt_b200_ctx *c, int n0, int np, int grid_threads)
     return 0;
 }
 
+/* ANAGLYPH_3D (ndt.c:634-646): the pixel is rendered once per eye and the two colours are
+ * mixed into red (left) and blue (right) */
+__global__ void k_anaglyph(const double *left, const double *right, int n, double *out_f64, uint8_t *out_u8)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double *l = left + 4 * (size_t)p, *r = right + 4 * (size_t)p;
+    const double cr = 0.299 * l[0] + 0.587 * l[1] + 0.114 * l[2];
+    const double cb = 0.299 * r[0] + 0.587 * r[1] + 0.114 * r[2];
+    if (out_f64) {
+        double2 *d = reinterpret_cast<double2 *>(out_f64 + 4 * (size_t)p);
+        d[0] = make_double2(cr, 0.0);
+        d[1] = make_double2(cb, 1.0);
+    }
+    if (out_u8) reinterpret_cast<uchar4 *>(out_u8)[p] = make_uchar4(d2c(cr), d2c(0.0), d2c(cb), d2c(1.0));
+}
+
+static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
+                       void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
+                       void *d_obj_id, void *d_inv_depth, bool first, bool last);
+
 extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                                     void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
                                     void *d_obj_id, void *d_inv_depth)
 {
     if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    if (!c->have_scene) return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_launch_tile before ndt_b200_upload");
+    if (c->hdr.stereo_mode != NDT_ANAGLYPH_3D) {
+        c->sc.eye_override = 0;
+        return launch_pass(c, x0, y0, tw, th, d_rgba_f64, d_rgba_u8, d_hit, d_obj_id, d_inv_depth, true, true);
+    }
+    const size_t px = (size_t)(tw > 0 ? tw : 0) * (size_t)(th > 0 ? th : 0);
+    int r = grow(c, (void **)&c->d_ana, &c->ana_bytes, 2 * px * 32 + 64);
+    if (r) return r;
+    double *dl = (double *)c->d_ana, *dr = dl + 4 * px;
+    c->sc.eye_override = 1;         /* depth and the hit / id buffers come from the left eye (ndt.c:637) */
+    r = launch_pass(c, x0, y0, tw, th, dl, NULL, d_hit, d_obj_id, d_inv_depth, true, false);
+    if (r) { c->sc.eye_override = 0; return r; }
+    const ndt_b200_stats left = c->last;
+    c->sc.eye_override = 2;
+    r = launch_pass(c, x0, y0, tw, th, dr, NULL, NULL, NULL, NULL, false, true);
+    c->sc.eye_override = 0;
+    if (r) return r;
+    c->last.rays_bounce += left.rays_bounce;
+    c->last.launches += left.launches + 1;
+    if (left.generations > c->last.generations) c->last.generations = left.generations;
+    k_anaglyph<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(dl, dr, (int)px, (double *)d_rgba_f64, (uint8_t *)d_rgba_u8);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    return 0;
+}
+
+static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
+                       void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
+                       void *d_obj_id, void *d_inv_depth, bool first, bool last)
+{
     if (!c->have_scene) return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_launch_tile before ndt_b200_upload");
     const ndt_flat_header &h = c->hdr;
     if (tw <= 0 || th <= 0 || x0 < 0 || y0 < 0 || x0 + tw > h.width || y0 + th > h.height)
@@ -362,8 +421,10 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     cudaStream_t st = c->stream;
     c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0; c->h_ctr[4] = 0; c->h_ctr[5] = 0;
     CK(cudaMemcpyAsync(c->d_ctr, c->h_ctr, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
-    CK(cudaEventRecord(c->ev0, st));
+    if (first) {
+        CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(c->ev0, st));
+    }
 
     /* generation starts, for the backward fold */
     int gstart[1024], gcount[1024], ngen = 0;
@@ -466,8 +527,10 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
                                                    (double *)d_rgba_f64, (uint8_t *)d_rgba_u8, c->d_stats);
     ++launches;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, st));
-    CK(cudaMemcpyAsync(c->h_stats, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (last) {
+        CK(cudaEventRecord(c->ev1, st));
+        CK(cudaMemcpyAsync(c->h_stats, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    }
 
     memset(&c->last, 0, sizeof c->last);
     c->last.rays_primary = (uint64_t)tw * th;
@@ -484,6 +547,7 @@ extern "C" int ndt_b200_sync(ndt_b200_ctx *c)
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last.device_ms = ms;
+    c->last.rays_primary = c->h_stats[5];     /* pixels that were traced (all but HIDEF_3D's blanking rows), per eye */
     c->last.rays_shadow = c->h_stats[0];
     c->last.flops = c->h_stats[1];
     c->last.rays_ref = c->h_stats[2];
@@ -666,16 +730,15 @@ extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_
 {
     (void)threads; (void)aa_diff; (void)aa_depth; (void)name; (void)depth_name;
     if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
-    if (stereo_mode != 0) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "stereo mode %d: only MONO (ndt.c:46) is on the device path", stereo_mode);
     static ndt_b200_ctx *ctx = NULL;     /* one context per process, like the reference's global kdtree */
     int r;
     if (!ctx && (r = ndt_b200_init(0, &ctx))) return r;
     ndt_flat_scene *fs = NULL;
-    if ((r = ndt_b200_flatten(scene, kdtree, width, height, max_optic_depth, specular, host, &fs))) return r;
+    if ((r = ndt_b200_flatten_view(scene, kdtree, width, height, max_optic_depth, specular, stereo_mode, host, &fs))) return r;
     /* render_image rescales the camera in place (ndt.c:925-926); callers rely on it */
     {
         ndtabi_scene *scn = (ndtabi_scene *)scene;
-        const double s = width / (double)height;
+        const double s = stereo_mode != NDT_HIDEF_3D ? width / (double)height : width / (double)1080;
         const int n = scn->cam.dirX.n, k = (n + 1) / 2;
         for (int i = 0; i < 2 * k; ++i) scn->cam.dirX.v[i] = scn->cam.dirX.v[i] * s;
     }

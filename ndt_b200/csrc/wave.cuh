@@ -17,6 +17,7 @@
 
 namespace ndt {
 
+constexpr uint32_t REC_UNTRACED = 2u;
 constexpr int CHILD_NONE = -1;
 constexpr int CHILD_BLACK = -2;   /* child cut by pixel_frac < 1/512 or depth 0 (ndt.c:336-341): colour (0,0,0), no trace */
 
@@ -27,7 +28,8 @@ struct RayRec {
     int32_t child_refl;
     int32_t child_refr;
     uint32_t nrays;       /* trace_kd calls of this ray's subtree (after resolve) */
-    uint32_t flags;       /* bit0: shaded (hit an object farther than EPSILON) */
+    uint32_t flags;       /* bit0: shaded (hit an object farther than EPSILON); REC_UNTRACED: no ray was traced
+                             (tile padding, HIDEF_3D blanking rows ndt.c:619-626) */
 };                        /* 80 bytes */
 
 template <int NP> struct RayIn {  /* queue entry of generation >= 1 */

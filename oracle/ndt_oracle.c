@@ -881,6 +881,7 @@ typedef struct {
     const void *blob;
     int x0, y0, tw, th, row0, rows_step;
     double *rgba; uint8_t *u8; uint8_t *hit; int32_t *id; double *inv_depth;
+    int eye_override;   /* 0, or 1 / 2: the left / right pass of ANAGLYPH_3D */
     uint64_t st[6]; /* primary, bounce, shadow, rays_ref, samples, reserved */
 } job;
 
@@ -897,26 +898,78 @@ static void *render_rows(void *arg)
         int j = J->y0 + ty;
         for (int tx = 0; tx < J->tw; ++tx) {
             int i = J->x0 + tx;
-            double x = (double)i / (double)W_ - 0.5;          /* ndt.c:632 */
-            double y = -((double)j / (double)H_ - 0.5);       /* ndt.c:633 */
-            double pixel[MAXD], tmp[MAXD], look[MAXD];
-            /* camera_target_point, camera.c:557-575 */
-            vcopy(pixel, corig, np);
-            vscale(cdx, x, tmp, np); vadd(pixel, tmp, pixel, np);
-            vscale(cdy, y, tmp, np); vadd(pixel, tmp, pixel, np);
-            if (w->h->use_focal) {
-                vsub(pixel, cpos, tmp, np);
-                vscale(tmp, w->h->focal_scale, tmp, np);
-                vadd(cpos, tmp, pixel, np);
+            double pixel[MAXD], tmp[MAXD], look[MAXD], eye[MAXD];
+            int blank = 0;
+            if (!w->h->off_view) {
+                double x = (double)i / (double)W_ - 0.5;          /* ndt.c:632 */
+                double y = -((double)j / (double)H_ - 0.5);       /* ndt.c:633 */
+                /* camera_target_point, camera.c:557-575 */
+                vcopy(pixel, corig, np);
+                vscale(cdx, x, tmp, np); vadd(pixel, tmp, pixel, np);
+                vscale(cdy, y, tmp, np); vadd(pixel, tmp, pixel, np);
+                if (w->h->use_focal) {
+                    vsub(pixel, cpos, tmp, np);
+                    vscale(tmp, w->h->focal_scale, tmp, np);
+                    vadd(cpos, tmp, pixel, np);
+                }
+                vcopy(eye, cpos, np);
+            } else {
+                /* render_pixel (ndt.c:578-653) + camera_target_point (camera.c:504-581) + the eye of
+                 * get_pixel_color (ndt.c:488-525), from the per-column / per-row tables the flattener
+                 * filled with the host's libm (ndt_flat.h, version 5) */
+                const double *ext = NDT_FLAT_PTR(J->blob, const double, w->h->off_view);
+                const double *col = ext + 5 * np + (size_t)i * 4;
+                const double *row = ext + 5 * np + (size_t)W_ * 4 + (size_t)j * 6;
+                const double x = col[0], y = row[0];
+                blank = row[4] != 0.0;
+                if (w->h->cam_type == NDT_CAM_NORMAL) {
+                    vcopy(pixel, corig, np);
+                    vscale(cdx, x, tmp, np); vadd(pixel, tmp, pixel, np);
+                    vscale(cdy, y, tmp, np); vadd(pixel, tmp, pixel, np);
+                    if (w->h->use_focal) {
+                        vsub(pixel, cpos, tmp, np);
+                        vscale(tmp, w->h->focal_scale, tmp, np);
+                        vadd(cpos, tmp, pixel, np);
+                    }
+                } else {
+                    const double dist = w->h->cam_dist;
+                    double vx, vy, vz;
+                    if (w->h->cam_type == NDT_CAM_VR) {           /* camera.c:507-529 */
+                        vx = dist * col[1] * row[2];
+                        vy = dist * row[1];
+                        vz = dist * col[2] * row[2];
+                    } else {                                      /* camera.c:530-556 */
+                        vx = dist * col[1];
+                        vy = row[3];
+                        vz = dist * col[2];
+                    }
+                    vcopy(pixel, cpos, np);
+                    vscale(ext + 2 * np, vx, tmp, np); vadd(pixel, tmp, pixel, np);
+                    vscale(ext + 3 * np, vy, tmp, np); vadd(pixel, tmp, pixel, np);
+                    vscale(ext + 4 * np, vz, tmp, np); vadd(pixel, tmp, pixel, np);
+                }
+                const int e = J->eye_override ? J->eye_override : ((int)col[3] | (int)row[5]);
+                if (e == 0) vcopy(eye, cpos, np);
+                else if (w->h->view_eyes)
+                    vcopy(eye, ext + 5 * np + (size_t)W_ * 4 + (size_t)H_ * 6 + ((size_t)i * 2 + (size_t)(e - 1)) * np, np);
+                else vcopy(eye, ext + (size_t)(e - 1) * np, np);
             }
-            vsub(pixel, cpos, look, np);
+            size_t p = (size_t)ty * J->tw + tx;
+            if (blank) {                                      /* ndt.c:619-626: black, nothing traced */
+                if (J->rgba) memset(J->rgba + 4 * p, 0, 32);
+                if (J->u8) memset(J->u8 + 4 * p, 0, 4);
+                if (J->hit) J->hit[p] = 0;
+                if (J->id) J->id[p] = -1;
+                if (J->inv_depth) J->inv_depth[p] = 0.0;
+                continue;
+            }
+            vsub(pixel, eye, look, np);
             vunit(look, np);
             raycnt rc = {0, 0, 0};
             double l[4], out[4];
             int ph = 0, pid = -1; double pd = -1;
-            ray_color(w, mask, &rc, cpos, look, l, 1.0, w->h->max_optic_depth, 1, &ph, &pid, &pd);
+            ray_color(w, mask, &rc, eye, look, l, 1.0, w->h->max_optic_depth, 1, &ph, &pid, &pd);
             int ns = replay_samples(l, out);
-            size_t p = (size_t)ty * J->tw + tx;
             if (J->rgba) memcpy(J->rgba + 4 * p, out, sizeof out);
             if (J->u8) for (int k = 0; k < 4; ++k) J->u8[4 * p + k] = d2c(out[k]);
             if (J->hit) J->hit[p] = (uint8_t)ph;
@@ -932,12 +985,10 @@ static void *render_rows(void *arg)
 }
 
 /* stats[5]: rays_primary, rays_bounce, rays_shadow, rays_ref, samples */
-int ndo_render(const void *blob, int x0, int y0, int tw, int th, int threads,
-               double *rgba, uint8_t *u8, uint8_t *hit, int32_t *id, double *inv_depth,
-               uint64_t *stats)
+static int render_pass(const void *blob, int x0, int y0, int tw, int th, int threads, int eye_override,
+                       double *rgba, uint8_t *u8, uint8_t *hit, int32_t *id, double *inv_depth,
+                       uint64_t *stats)
 {
-    const ndt_flat_header *h = blob;
-    if (!h || h->magic != NDT_FLAT_MAGIC || h->version != NDT_FLAT_VERSION) return -1;
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;
     job *jobs = calloc((size_t)threads, sizeof *jobs);
@@ -947,15 +998,45 @@ int ndo_render(const void *blob, int x0, int y0, int tw, int th, int threads,
         J->blob = blob; J->x0 = x0; J->y0 = y0; J->tw = tw; J->th = th;
         J->row0 = t; J->rows_step = threads;
         J->rgba = rgba; J->u8 = u8; J->hit = hit; J->id = id; J->inv_depth = inv_depth;
+        J->eye_override = eye_override;
         if (threads > 1) pthread_create(&thr[t], NULL, render_rows, J);
         else render_rows(J);
     }
-    if (stats) memset(stats, 0, 5 * sizeof *stats);
     for (int t = 0; t < threads; ++t) {
         if (threads > 1) pthread_join(thr[t], NULL);
         if (stats) for (int k = 0; k < 5; ++k) stats[k] += jobs[t].st[k];
     }
     free(jobs); free(thr);
+    return 0;
+}
+
+/* stats[5]: rays_primary, rays_bounce, rays_shadow, rays_ref, samples */
+int ndo_render(const void *blob, int x0, int y0, int tw, int th, int threads,
+               double *rgba, uint8_t *u8, uint8_t *hit, int32_t *id, double *inv_depth,
+               uint64_t *stats)
+{
+    const ndt_flat_header *h = blob;
+    if (!h || h->magic != NDT_FLAT_MAGIC || h->version != NDT_FLAT_VERSION) return -1;
+    if (stats) memset(stats, 0, 5 * sizeof *stats);
+    if (h->stereo_mode != NDT_ANAGLYPH_3D)
+        return render_pass(blob, x0, y0, tw, th, threads, 0, rgba, u8, hit, id, inv_depth, stats);
+    /* ANAGLYPH_3D, ndt.c:634-646: one render per eye, mixed into red (left) and blue (right);
+     * depth (and our hit / id buffers) from the left eye */
+    const size_t px = (size_t)tw * th;
+    double *l = malloc(px * 32), *r = malloc(px * 32);
+    if (!l || !r) { free(l); free(r); return -2; }
+    render_pass(blob, x0, y0, tw, th, threads, 1, l, NULL, hit, id, inv_depth, stats);
+    render_pass(blob, x0, y0, tw, th, threads, 2, r, NULL, NULL, NULL, NULL, stats);
+    for (size_t p = 0; p < px; ++p) {
+        double out[4];
+        out[0] = 0.299 * l[4 * p] + 0.587 * l[4 * p + 1] + 0.114 * l[4 * p + 2];
+        out[1] = 0;
+        out[2] = 0.299 * r[4 * p] + 0.587 * r[4 * p + 1] + 0.114 * r[4 * p + 2];
+        out[3] = 1.0;
+        if (rgba) memcpy(rgba + 4 * p, out, sizeof out);
+        if (u8) for (int k = 0; k < 4; ++k) u8[4 * p + k] = d2c(out[k]);
+    }
+    free(l); free(r);
     return 0;
 }
 

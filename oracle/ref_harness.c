@@ -220,8 +220,37 @@ int refh_num_items(void) { return g_nflat; }
 void *refh_object_get_bounds_ptr(void) { return (void *)object_get_bounds; }
 void refh_set_specular(int on) { specular_enabled = on; }
 
+void *refh_rotate2_ptr(void) { return (void *)vectNd_rotate2; }
+
+/* what main() does for -V / -P before camera_aim (ndt.c:1915-1925): camera type and fields of view */
+int refh_set_camera(int type, double h_fov, double v_fov)
+{
+    if (!g_frame_open)
+        return -1;
+    refh_reaim();
+    g_scn.cam.type = type;
+    if (type != CAMERA_NORMAL) {
+        g_scn.cam.hFov = h_fov;
+        g_scn.cam.vFov = v_fov;
+    }
+    hush(1);
+    camera_aim(&g_scn.cam);
+    hush(0);
+    g_dirx_scaled = 0;
+    save_dirx();
+    return 0;
+}
+
+int refh_render_ex(int w, int h, int threads, int max_optic_depth, int stereo, double *rgba, double *seconds);
+
 /* render_image (ndt.c:900) with samples=1, MONO; copies the fp64 RGBA frame */
 int refh_render(int w, int h, int threads, int max_optic_depth, double *rgba, double *seconds)
+{
+    return refh_render_ex(w, h, threads, max_optic_depth, REF_MONO, rgba, seconds);
+}
+
+/* the same for any stereo_mode of ndt.c:46-48 */
+int refh_render_ex(int w, int h, int threads, int max_optic_depth, int stereo, double *rgba, double *seconds)
 {
     if (!g_frame_open)
         return -1;
@@ -230,7 +259,7 @@ int refh_render(int w, int h, int threads, int max_optic_depth, double *rgba, do
     struct timespec a, b;
     hush(1);
     clock_gettime(CLOCK_MONOTONIC, &a);
-    render_image(&g_scn, "oracle", NULL, w, h, 1, REF_MONO, threads, 20, 4, max_optic_depth, NULL, NULL);
+    render_image(&g_scn, "oracle", NULL, w, h, 1, (ref_stereo_mode)stereo, threads, 20, 4, max_optic_depth, NULL, NULL);
     clock_gettime(CLOCK_MONOTONIC, &b);
     hush(0);
     g_dirx_scaled = 1;

@@ -49,6 +49,9 @@ class RefHarness:
         L.refh_kdtree.restype = C.c_void_p
         L.refh_object_get_bounds_ptr.restype = C.c_void_p
         L.refh_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.refh_render_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.refh_set_camera.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.refh_rotate2_ptr.restype = C.c_void_p
         L.refh_primary.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refh_trace_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.refh_ray_count.restype = C.c_long
@@ -129,15 +132,25 @@ class RefHarness:
         return self.lib.refh_num_items()
 
     # -- the reference's results ---------------------------------------------
-    def render(self, w, h, threads=None, max_optic_depth=128):
-        """fp64 RGBA [h, w, 4] from the reference's render_image, and seconds."""
+    def render(self, w, h, threads=None, max_optic_depth=128, stereo=0):
+        """fp64 RGBA [h, w, 4] from the reference's render_image (any stereo_mode of ndt.c:46-48), and seconds."""
         threads = threads or os.cpu_count()
         out = np.empty((h, w, 4), dtype=np.float64)
         sec = C.c_double(0)
-        r = self.lib.refh_render(w, h, threads, max_optic_depth, out.ctypes.data, C.byref(sec))
+        r = self.lib.refh_render_ex(w, h, threads, max_optic_depth, stereo, out.ctypes.data, C.byref(sec))
         if r != 0:
-            raise RuntimeError(f"refh_render -> {r}")
+            raise RuntimeError(f"refh_render_ex -> {r}")
         return out, sec.value
+
+    def set_camera(self, cam_type, h_fov=0.0, v_fov=0.0):
+        """-V / -P of the reference's command line (ndt.c:1915-1925): camera type + fields of view, re-aimed."""
+        r = self.lib.refh_set_camera(cam_type, h_fov, v_fov)
+        if r != 0:
+            raise RuntimeError(f"refh_set_camera -> {r}")
+
+    @property
+    def rotate2_ptr(self):
+        return self.lib.refh_rotate2_ptr()
 
     def primary(self, w, h):
         hit = np.empty((h, w), dtype=np.uint8)

@@ -15,7 +15,7 @@ using namespace ndt;
 
 template <int NP>
 static int run(const void *blob, int x0, int y0, int tw, int th, double *f64, uint8_t *u8,
-               uint8_t *hit, int32_t *id, double *dep, uint64_t *stats)
+               uint8_t *hit, int32_t *id, double *dep, uint64_t *stats, int eye_override = 0)
 {
     const ndt_flat_header *h = (const ndt_flat_header *)blob;
     const char *b = (const char *)blob;
@@ -36,6 +36,9 @@ static int run(const void *blob, int x0, int y0, int tw, int th, double *f64, ui
     for (int k = 0; k < 4; ++k) s.bg[k] = h->bg[k];
     for (int k = 0; k < 3; ++k) s.ambient[k] = h->ambient[k];
     s.focal_scale = h->focal_scale;
+    s.view = h->off_view ? (const double *)(b + h->off_view) : nullptr;
+    s.cam_type = h->cam_type; s.stereo_mode = h->stereo_mode; s.view_eyes = h->view_eyes;
+    s.eye_override = eye_override; s.cam_dist = h->cam_dist;
 
     const int bpr = (tw + 7) / 8, brows = (th + 3) / 4, n0 = bpr * brows * 32;
     std::vector<RayRec> rec(n0);
@@ -61,7 +64,7 @@ static int run(const void *blob, int x0, int y0, int tw, int th, double *f64, ui
                 int blk = r >> 5, lane = r & 31;
                 tx = (blk % bpr) * 8 + (lane & 7); ty = (blk / bpr) * 4 + (lane >> 3);
                 active = tx < tw && ty < th;
-                if (active) primary_ray<NP>(s, x0 + tx, y0 + ty, o, v);
+                if (active) active = primary_ray<NP>(s, x0 + tx, y0 + ty, o, v);
             } else {
                 const RayIn<NP> &in = rays[start + r - n0];
                 for (int i = 0; i < NP; ++i) { o[i] = in.o[i]; v[i] = in.v[i]; }
@@ -69,6 +72,15 @@ static int run(const void *blob, int x0, int y0, int tw, int th, double *f64, ui
             }
             RayRec rc; memset(&rc, 0, sizeof rc);
             rc.child_refl = rc.child_refr = CHILD_NONE;
+            if (!active) {
+                rc.flags = REC_UNTRACED;
+                if (gen == 0 && tx < tw && ty < th) {     /* a pixel of the frame that is not traced */
+                    size_t p = (size_t)ty * tw + tx;
+                    if (hit) hit[p] = 0;
+                    if (id) id[p] = -1;
+                    if (dep) dep[p] = 0.0;
+                }
+            }
             if (active) {
                 Spawn<NP> sp; int ph = 0, pid = -1; double pd = -1; uint32_t nsh = 0;
                 process_ray<NP, true>(s, mb, o, v, frac, depth, rc, sp, ph, pid, pd, nsh, ovf, tally);
@@ -104,22 +116,52 @@ static int run(const void *blob, int x0, int y0, int tw, int th, double *f64, ui
             resolve_rec(r, r.child_refl >= 0 ? &rec[r.child_refl] : nullptr,
                         r.child_refr >= 0 ? &rec[r.child_refr] : nullptr, h->specular);
         }
-    uint64_t rays_ref = 0, samples = 0;
+    uint64_t rays_ref = 0, samples = 0, traced = 0;
     for (int p = 0; p < tw * th; ++p) {
         int tx = p % tw, ty = p / tw;
         int slot = ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7);
         RayRec r = rec[slot];
         resolve_rec(r, r.child_refl >= 0 ? &rec[r.child_refl] : nullptr,
                     r.child_refr >= 0 ? &rec[r.child_refr] : nullptr, h->specular);
-        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4];
-        int ns = replay_samples(l, o);
+        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4] = { 0.0, 0.0, 0.0, 0.0 };
+        int ns = (r.flags & REC_UNTRACED) ? 0 : replay_samples(l, o);
         if (f64) memcpy(f64 + 4 * (size_t)p, o, sizeof o);
         if (u8) for (int k = 0; k < 4; ++k) u8[4 * (size_t)p + k] = d2c(o[k]);
         rays_ref += (uint64_t)r.nrays * ns; samples += ns;
+        traced += (r.flags & REC_UNTRACED) ? 0 : 1;
     }
     if (stats) {
-        stats[0] = (uint64_t)tw * th; stats[1] = rays.size(); stats[2] = shadow;
+        stats[0] = traced; stats[1] = rays.size(); stats[2] = shadow;
         stats[3] = rays_ref; stats[4] = samples; stats[5] = tally.f; stats[6] = gstart.size(); stats[7] = ovf;
+    }
+    return 0;
+}
+
+template <int NP>
+static int run_view(const void *blob, int x0, int y0, int tw, int th, double *f64, uint8_t *u8,
+                    uint8_t *hit, int32_t *id, double *dep, uint64_t *stats)
+{
+    const ndt_flat_header *h = (const ndt_flat_header *)blob;
+    if (h->stereo_mode != NDT_ANAGLYPH_3D) return run<NP>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
+    /* ANAGLYPH_3D (ndt.c:634-646), like ndt_b200_launch_tile: one pass per eye, then the mix */
+    const size_t px = (size_t)tw * th;
+    std::vector<double> l(px * 4), r(px * 4);
+    uint64_t s1[8] = {0}, s2[8] = {0};
+    run<NP>(blob, x0, y0, tw, th, l.data(), nullptr, hit, id, dep, s1, 1);
+    run<NP>(blob, x0, y0, tw, th, r.data(), nullptr, nullptr, nullptr, nullptr, s2, 2);
+    for (size_t p = 0; p < px; ++p) {
+        double o[4];
+        o[0] = 0.299 * l[4 * p] + 0.587 * l[4 * p + 1] + 0.114 * l[4 * p + 2];
+        o[1] = 0;
+        o[2] = 0.299 * r[4 * p] + 0.587 * r[4 * p + 1] + 0.114 * r[4 * p + 2];
+        o[3] = 1.0;
+        if (f64) memcpy(f64 + 4 * p, o, sizeof o);
+        if (u8) for (int k = 0; k < 4; ++k) u8[4 * p + k] = d2c(o[k]);
+    }
+    if (stats) {
+        for (int k = 0; k < 6; ++k) stats[k] = s1[k] + s2[k];
+        stats[6] = s1[6] > s2[6] ? s1[6] : s2[6];
+        stats[7] = s1[7] | s2[7];
     }
     return 0;
 }
@@ -129,11 +171,11 @@ extern "C" int emu_render(const void *blob, int x0, int y0, int tw, int th, doub
 {
     const ndt_flat_header *h = (const ndt_flat_header *)blob;
     switch (h->npad) {
-    case 4: return run<4>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
-    case 6: return run<6>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
-    case 8: return run<8>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
-    case 10: return run<10>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
-    case 12: return run<12>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
+    case 4: return run_view<4>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
+    case 6: return run_view<6>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
+    case 8: return run_view<8>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
+    case 10: return run_view<10>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
+    case 12: return run_view<12>(blob, x0, y0, tw, th, f64, u8, hit, id, dep, stats);
     }
     return -1;
 }

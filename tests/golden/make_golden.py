@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 import ndt_b200  # noqa: E402
 from oracle.refharness import RefHarness, rgba_f64_to_u8  # noqa: E402
-from scenes import CASES  # noqa: E402
+from scenes import CASES, H_FOV, V_FOV  # noqa: E402
 
 
 def sha(a):
@@ -98,18 +98,30 @@ def main():
         if frames <= 0:
             frames = 300
         R.begin_frame(c.dims, c.frame, frames, c.cfg)
-        flat = ndt_b200.flatten(R.scene_ptr, R.kdtree_ptr, c.w, c.h, 128, 1, R.get_bounds_ptr)
-        kats = make_kats(R, flat, c, rng)
-        img, _ = R.render(c.w, c.h, threads=os.cpu_count())
-        hit, oid, dist = R.primary(c.w, c.h)
+        view = c.cam != 0 or c.stereo != 0
+        if view:
+            R.set_camera(c.cam, H_FOV, V_FOV)
+        flat = ndt_b200.flatten(R.scene_ptr, R.kdtree_ptr, c.w, c.h, 128, 1, R.get_bounds_ptr,
+                                stereo_mode=c.stereo, host_rotate2=R.rotate2_ptr)
+        kats = [] if view else make_kats(R, flat, c, rng)
+        img, _ = R.render(c.w, c.h, threads=os.cpu_count(), stereo=c.stereo)
+        if view:
+            # hit / id buffers of the new views: the oracle's, pinned through the fp64 image it shares with them
+            hit = np.zeros((c.h, c.w), np.uint8); oid = np.zeros((c.h, c.w), np.int32)
+            if c.stereo == 4:
+                img[1080:1126, :, 3] = 0.0     # blanking rows: alpha is uninitialised stack in the reference (ndt.c:623)
+        else:
+            hit, oid, dist = R.primary(c.w, c.h)
         R.end_frame()
-        with open(os.path.join(HERE, c.key + ".kat.json"), "w") as f:
-            json.dump(kats, f)
+        if not view:
+            with open(os.path.join(HERE, c.key + ".kat.json"), "w") as f:
+                json.dump(kats, f)
         flat.save(os.path.join(HERE, c.key + ".ndsf.gz"))
         u8 = rgba_f64_to_u8(img)
         pts = [(0, 0), (c.h // 2, c.w // 2), (c.h - 1, c.w - 1), (c.h // 3, (2 * c.w) // 3)]
         out[c.key] = {
             "scene": c.scene, "dims": c.dims, "cfg": c.cfg, "frame": c.frame, "w": c.w, "h": c.h,
+            "cam": c.cam, "stereo": c.stereo, "view": view,
             "flat_bytes": len(flat), "n_items": flat.header.n_items, "n_objects": flat.header.n_objects,
             "n_nodes": flat.header.n_nodes, "n_leaf_refs": flat.header.n_leaf_refs,
             "sha_f64": sha(img), "sha_u8": sha(u8), "sha_hit": sha(hit), "sha_id": sha(oid),

@@ -8,9 +8,13 @@ finishes in about a second.  `cfg` rows map to BASELINE.json configs:
   config3  random -d 6 (n=40, the reference kd builder explodes beyond ~200)
   config4  balls -d 5            config5  mixed10d (our C twin of the 10-D YAML)
 """
+import math
 from collections import namedtuple
 
-Case = namedtuple("Case", "key scene dims cfg frame w h")
+# cam: camera.h:16-20 (0 NORMAL, 1 VR, 2 PANO); stereo: ndt.c:46-48 (0 MONO, 1 SIDE_SIDE_3D,
+# 2 OVER_UNDER_3D, 3 ANAGLYPH_3D, 4 HIDEF_3D)
+Case = namedtuple("Case", "key scene dims cfg frame w h cam stereo", defaults=(0, 0))
+H_FOV, V_FOV = 2.0 * math.pi, math.pi          # the defaults of -V / -P (ndt.c:1425-1426)
 
 CASES = [
     Case("config1_default4d", None, 4, None, 0, 160, 90),
@@ -26,4 +30,17 @@ CASES = [
     Case("mixed7d", "mixed10d", 7, None, 5, 96, 54),
     Case("mixed12d", "mixed10d", 12, None, 11, 64, 36),
 ]
+# the other cameras and the stereo modes of render_pixel, same scenes
+VIEW_CASES = [
+    Case("view_sidebyside4d", None, 4, None, 0, 96, 54, 0, 1),
+    Case("view_overunder7d", "mixed10d", 7, None, 5, 96, 54, 0, 2),
+    Case("view_anaglyph5d", "hypercube", 5, "hcube", 3, 64, 36, 0, 3),
+    Case("view_hidef4d", None, 4, None, 0, 24, 2205, 0, 4),
+    Case("view_vr5d", "hypercube", 5, "hcube", 3, 96, 54, 1, 0),
+    Case("view_pano7d", "mixed10d", 7, None, 5, 96, 54, 2, 0),
+    Case("view_vr_sidebyside4d", None, 4, None, 0, 96, 54, 1, 1),
+    Case("view_pano_anaglyph4d", None, 4, None, 0, 48, 28, 2, 3),
+]
+BASE_CASES = list(CASES)
+CASES = CASES + VIEW_CASES
 BY_KEY = {c.key: c for c in CASES}

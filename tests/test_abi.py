@@ -35,13 +35,13 @@ def test_version_and_error_strings():
 
 def test_struct_sizes_of_python_mirror():
     assert C.sizeof(ndt_b200.Stats) == 80
-    assert C.sizeof(ndt_b200.FlatHeader) == 224
+    assert C.sizeof(ndt_b200.FlatHeader) == 256
 
 
 def test_header_compiles_as_c_and_cxx(tmp_path):
     for comp, ext, std in (("gcc", "c", "-std=gnu99"), ("g++", "cpp", "-std=c++17")):
         f = tmp_path / f"t.{ext}"
-        f.write_text('#include "ndt_abi.h"\n#include "ndt_b200.h"\nint main(void){return (sizeof(ndt_flat_header)==224 && sizeof(ndt_b200_stats)==80 && sizeof(ndt_flat_object)==96 && sizeof(ndt_flat_node)==32 && sizeof(ndt_flat_light)==56)?0:1;}\n')
+        f.write_text('#include "ndt_abi.h"\n#include "ndt_b200.h"\nint main(void){return (sizeof(ndt_flat_header)==256 && sizeof(ndt_b200_stats)==80 && sizeof(ndt_flat_object)==96 && sizeof(ndt_flat_node)==32 && sizeof(ndt_flat_light)==56)?0:1;}\n')
         exe = tmp_path / f"t_{ext}"
         subprocess.run([comp, std, "-I" + os.path.join(ROOT, "include"), str(f), "-o", str(exe)], check=True)
         assert subprocess.run([str(exe)]).returncode == 0

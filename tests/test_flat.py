@@ -52,16 +52,25 @@ def test_retarget_needs_same_aspect():
 
 
 def test_flatten_refuses_what_the_device_cannot_do(ref):
-    """Unknown plugins / area lights / VR cameras are hard errors, not CPU fallbacks."""
+    """Unknown camera types / area lights / a VR stereo view without the host's vectNd_rotate2 are hard
+    errors, not CPU fallbacks."""
     import numpy as np
     ref.open_scene(None)
     ref.begin_frame(4, 0, 300, None)
     try:
-        # CAMERA_VR = 1: camera.type is the first int of scene.cam (offset 16)
+        # camera.type is the first int of scene.cam (offset 16); camera.h:16-20 knows 0..2
         cam_type = C.c_int.from_address(ref.scene_ptr + 16)
-        cam_type.value = 1
+        cam_type.value = 7
         with pytest.raises(ndt_b200.NdtB200Error) as e:
             ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, 64, 36, 128, 1, ref.get_bounds_ptr)
+        assert e.value.code == -2
+        cam_type.value = 1          # CAMERA_VR side by side: the eye is rotated per column by the host's vectNd_rotate2
+        with pytest.raises(ndt_b200.NdtB200Error) as e:
+            ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, 64, 36, 128, 1, ref.get_bounds_ptr,
+                             stereo_mode=ndt_b200.SIDE_SIDE_3D)
+        assert e.value.code == -1
+        with pytest.raises(ndt_b200.NdtB200Error) as e:
+            ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, 64, 36, 128, 1, ref.get_bounds_ptr, stereo_mode=9)
         assert e.value.code == -2
         cam_type.value = 0
         # first light -> LIGHT_DISK (4): lights[0]->type at offset 248

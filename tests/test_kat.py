@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, load_flat
-from scenes import CASES
+from scenes import BASE_CASES as CASES
 
 
 def load_kats(key):

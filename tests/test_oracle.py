@@ -26,12 +26,14 @@ def test_oracle_matches_reference_digests(case, golden, oracle_lib):
     for s in g["samples"]:
         got = [float(v).hex() for v in out.f64[s["y"], s["x"]]]
         assert got == s["rgba_hex"], f"pixel ({s['x']},{s['y']})"
-        assert int(out.hit[s["y"], s["x"]]) == s["hit"] and int(out.id[s["y"], s["x"]]) == s["id"]
-    assert sha(out.hit) == g["sha_hit"]
-    assert sha(out.id) == g["sha_id"]
+        if not g.get("view"):
+            assert int(out.hit[s["y"], s["x"]]) == s["hit"] and int(out.id[s["y"], s["x"]]) == s["id"]
     assert sha(out.f64) == g["sha_f64"]
     assert sha(out.u8) == g["sha_u8"]
-    assert int(out.hit.sum()) == g["hit_pixels"]
+    if not g.get("view"):       # hit / id of the reference exist for MONO + CAMERA_NORMAL (refh_primary)
+        assert sha(out.hit) == g["sha_hit"]
+        assert sha(out.id) == g["sha_id"]
+        assert int(out.hit.sum()) == g["hit_pixels"]
 
 
 def test_oracle_is_thread_count_independent(oracle_lib):
@@ -60,16 +62,26 @@ def test_oracle_matches_live_reference(case, ref, oracle_lib):
     ref.open_scene(case.scene)
     frames = ref.scene_frames(case.dims, case.cfg) if case.scene else 300
     ref.begin_frame(case.dims, case.frame, frames if frames > 0 else 300, case.cfg)
+    view = case.cam != 0 or case.stereo != 0
     try:
-        flat = ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, case.w, case.h, 128, 1, ref.get_bounds_ptr)
-        img, _ = ref.render(case.w, case.h)
-        hit, oid, dist = ref.primary(case.w, case.h)
+        if view:
+            from scenes import H_FOV, V_FOV
+            ref.set_camera(case.cam, H_FOV, V_FOV)
+        flat = ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, case.w, case.h, 128, 1, ref.get_bounds_ptr,
+                                stereo_mode=case.stereo, host_rotate2=ref.rotate2_ptr)
+        img, _ = ref.render(case.w, case.h, stereo=case.stereo)
+        if not view:
+            hit, oid, dist = ref.primary(case.w, case.h)
     finally:
         ref.end_frame()
     # the flattener is deterministic: same bytes as the committed fixture
     assert flat.blob == load_flat(case.key).blob
     out = oracle_render(oracle_lib, flat)
+    if case.stereo == 4:
+        img[1080:1126, :, 3] = 0.0      # blanking rows: alpha is uninitialised stack in the reference (ndt.c:623)
     assert bits_equal(out.f64, img)
+    if view:
+        return
     assert np.array_equal(out.hit, hit) and np.array_equal(out.id, oid)
     inv = np.where((oid >= 0) & (dist > 1e-4), 1.0 / np.where(dist > 0, dist, 1.0), 0.0)
     assert bits_equal(out.depth, inv)
