@@ -92,6 +92,12 @@ int ndt_b200_flatten(const void *scene, const void *kdtree, int width, int heigh
 int ndt_b200_flatten_view(const void *scene, const void *kdtree, int width, int height,
                           int max_optic_depth, int specular, int stereo_mode,
                           const ndt_b200_host_api *host, ndt_flat_scene **out);
+/* The scene for recursive anti-aliasing (-w / -a; render_image with the global recursive_aa set,
+ * ndt.c:921-926): header width/height are the (width+1) x (height+1) grid of corner samples.
+ * Render it with ndt_b200_render_aa. */
+int ndt_b200_flatten_aa(const void *scene, const void *kdtree, int width, int height,
+                        int max_optic_depth, int specular,
+                        const ndt_b200_host_api *host, ndt_flat_scene **out);
 void ndt_b200_free_flat(ndt_flat_scene *fs);
 /* structural check of a blob received from disk or another rank */
 int ndt_b200_flat_validate(const void *blob, size_t bytes);
@@ -130,6 +136,16 @@ int ndt_b200_sync(ndt_b200_ctx *ctx);
 int ndt_b200_last_stats(ndt_b200_ctx *ctx, ndt_b200_stats *stats);
 /* the stream all of a context's work is enqueued on (cudaStream_t as void*) */
 void *ndt_b200_stream(ndt_b200_ctx *ctx);
+
+/* Recursive (Whitted) anti-aliasing, the second half of render_image when recursive_aa is set
+ * (ndt.c:655-733, 1039-1088): the uploaded scene must come from ndt_b200_flatten_aa.  Renders the
+ * (W+1) x (H+1) corner samples, then refines every pixel whose four corners differ by more than
+ * aa_diff/255 (image_avg_dbl_pixels4, image.c:1175) level by level -- each level's new samples are
+ * one more wavefront over an explicit sample list -- down to steps of 1/2^aa_depth (ndt.c:663).
+ * Output: the W x H frame as the reference stores it, 8-bit RGBA through pixel_d2c (actual_img is an
+ * 8-bit image, ndt.c:940-942), plus optionally the fp64 colours before quantisation.  HOST buffers. */
+int ndt_b200_render_aa(ndt_b200_ctx *ctx, int aa_diff, int aa_depth,
+                       uint8_t *rgba_u8, double *rgba_f64, uint64_t *pixels_resampled, ndt_b200_stats *stats);
 
 /* Drop-in for render_image (ndt.c:900), same parameters and return value
  * (1).  `kdtree` is the extra argument: the reference reads its global

@@ -154,7 +154,8 @@ typedef struct ndt_flat_header {
     int32_t cam_type;               /* camera.h:16-20: 0 CAMERA_NORMAL, 1 CAMERA_VR, 2 CAMERA_PANO */
     int32_t stereo_mode;            /* ndt.c:46-48 */
     int32_t view_eyes;              /* eyes[] present */
-    int32_t reserved2;
+    int32_t aa_pad;                 /* 1: width/height are the (W+1) x (H+1) sample grid of the recursive
+                                       anti-aliasing pass (ndt.c:921-924), dirX scaled by W/H */
     uint64_t off_view;
     double cam_dist;                /* cam.focal_distance as passed to camera_target_point (ndt.c:515) */
 } ndt_flat_header;

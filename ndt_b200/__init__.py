@@ -63,7 +63,7 @@ class FlatHeader(C.Structure):
                 ("off_nodes", C.c_uint64), ("off_leaf_refs", C.c_uint64), ("off_inf", C.c_uint64),
                 ("off_lights", C.c_uint64),
                 ("cam_type", C.c_int32), ("stereo_mode", C.c_int32), ("view_eyes", C.c_int32),
-                ("reserved2", C.c_int32), ("off_view", C.c_uint64), ("cam_dist", C.c_double)]
+                ("aa_pad", C.c_int32), ("off_view", C.c_uint64), ("cam_dist", C.c_double)]
 
 
 _lib = None
@@ -84,6 +84,10 @@ def lib():
                                    C.POINTER(_HostApi), C.POINTER(C.c_void_p)]
     L.ndt_b200_flatten_view.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.POINTER(_HostApi), C.POINTER(C.c_void_p)]
+    L.ndt_b200_flatten_aa.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(_HostApi), C.POINTER(C.c_void_p)]
+    L.ndt_b200_render_aa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_uint64), C.POINTER(Stats)]
     L.ndt_b200_free_flat.argtypes = [C.c_void_p]
     L.ndt_b200_free_flat.restype = None
     L.ndt_b200_flat_validate.argtypes = [C.c_void_p, C.c_size_t]
@@ -174,6 +178,20 @@ def flatten(scene_ptr, kdtree_ptr, width, height, max_optic_depth=128, specular=
         L.ndt_b200_free_flat(out)
 
 
+def flatten_aa(scene_ptr, kdtree_ptr, width, height, max_optic_depth=128, specular=1, host_get_bounds=None):
+    """ndt_b200_flatten_aa: the (width+1) x (height+1) corner-sample grid of recursive anti-aliasing."""
+    L = lib()
+    host = _HostApi(host_get_bounds, None)
+    out = C.c_void_p()
+    _check(L.ndt_b200_flatten_aa(scene_ptr, kdtree_ptr, width, height, max_optic_depth, specular,
+                                 C.byref(host), C.byref(out)))
+    try:
+        total = C.c_uint64.from_address(out.value + 8).value
+        return FlatScene(C.string_at(out.value, total))
+    finally:
+        L.ndt_b200_free_flat(out)
+
+
 def kd_tree_build(kd_tree_ptr, kd_item_list_ptr):
     """ndt_b200_kd_tree_build: drop-in for kd_tree_build (kd-tree.c:421) on host structures."""
     return _check(lib().ndt_b200_kd_tree_build(kd_tree_ptr, kd_item_list_ptr))
@@ -252,6 +270,17 @@ class Context:
                                           _p(fr.hit), _p(fr.obj_id), _p(fr.inv_depth), C.byref(st)))
         fr.stats = st
         return fr
+
+    def render_aa(self, aa_diff=20, aa_depth=4, want_f64=False):
+        """ndt_b200_render_aa on a scene from flatten_aa: (u8 [H, W, 4], f64 or None, pixels resampled, stats)."""
+        h = self._flat.header
+        W, H = h.width - 1, h.height - 1
+        u8 = np.empty((H, W, 4), np.uint8)
+        f64 = np.empty((H, W, 4), np.float64) if want_f64 else None
+        n = C.c_uint64(0)
+        st = Stats()
+        _check(lib().ndt_b200_render_aa(self._h, aa_diff, aa_depth, u8.ctypes.data, _p(f64), C.byref(n), C.byref(st)))
+        return u8, f64, n.value, st
 
     def launch_tile(self, x0, y0, tw, th, d_f64=None, d_u8=None, d_hit=None, d_id=None, d_depth=None):
         """ndt_b200_launch_tile: outputs are DEVICE pointers (ints, e.g. tensor.data_ptr())."""

@@ -541,10 +541,31 @@ static void tmpvec_wrap(ndtabi_vec *v, double *store, int n)
     v->n = n;
 }
 
+static int flatten_impl(const void *scene_v, const void *kdtree_v, int width, int height,
+                        int max_optic_depth, int specular, int stereo_mode, int aa_pad,
+                        const ndt_b200_host_api *host, ndt_flat_scene **out);
+
 int ndt_b200_flatten_view(const void *scene_v, const void *kdtree_v, int width, int height,
                           int max_optic_depth, int specular, int stereo_mode,
                           const ndt_b200_host_api *host, ndt_flat_scene **out)
 {
+    return flatten_impl(scene_v, kdtree_v, width, height, max_optic_depth, specular, stereo_mode, 0, host, out);
+}
+
+/* recursive anti-aliasing (-w / -a, ndt.c:921-926): the initial image is one sample larger in each
+ * direction and normalised by width+1 / height+1, while cam.dirX is scaled by width/height */
+int ndt_b200_flatten_aa(const void *scene_v, const void *kdtree_v, int width, int height,
+                        int max_optic_depth, int specular,
+                        const ndt_b200_host_api *host, ndt_flat_scene **out)
+{
+    return flatten_impl(scene_v, kdtree_v, width, height, max_optic_depth, specular, NDT_MONO, 1, host, out);
+}
+
+static int flatten_impl(const void *scene_v, const void *kdtree_v, int out_width, int out_height,
+                        int max_optic_depth, int specular, int stereo_mode, int aa_pad,
+                        const ndt_b200_host_api *host, ndt_flat_scene **out)
+{
+    const int width = out_width + (aa_pad ? 1 : 0), height = out_height + (aa_pad ? 1 : 0);
     const ndtabi_scene *scn = scene_v;
     const ndtabi_kd_tree *kd = kdtree_v;
     fstate S, *st = &S;
@@ -573,6 +594,15 @@ int ndt_b200_flatten_view(const void *scene_v, const void *kdtree_v, int width, 
         goto done;
     }
     const int cam_type = scn->cam.type;
+    if (aa_pad && (cam_type != NDT_CAM_NORMAL || stereo_mode != NDT_MONO)) {
+        r = ndt_set_error(NDT_B200_E_UNSUPPORTED, "recursive anti-aliasing is on the device path for CAMERA_NORMAL + MONO only");
+        goto done;
+    }
+    if (aa_pad && scn->cam.aperture_radius != 0.0) {
+        r = ndt_set_error(NDT_B200_E_UNSUPPORTED, "recursive anti-aliasing with aperture_radius %g: the depth-of-field "
+                          "jitter draws from drand48 (ndt.c:528-542) and is not reproducible", scn->cam.aperture_radius);
+        goto done;
+    }
     const int has_view = cam_type != NDT_CAM_NORMAL || stereo_mode != NDT_MONO;
     /* VR / PANO in a stereo mode: the eye is rotated per column (ndt.c:519-525) */
     const int view_eyes = cam_type != NDT_CAM_NORMAL && stereo_mode != NDT_MONO;
@@ -680,7 +710,7 @@ int ndt_b200_flatten_view(const void *scene_v, const void *kdtree_v, int width, 
     H.off_leaf_refs = off; off = align16(off + st->leaf.n * 4);
     H.off_inf = off;      off = align16(off + (size_t)kd->inf_obj_num * 4);
     H.off_lights = off;   off = align16(off + (size_t)n_l * sizeof(ndt_flat_light));
-    H.cam_type = cam_type; H.stereo_mode = stereo_mode; H.view_eyes = view_eyes;
+    H.cam_type = cam_type; H.stereo_mode = stereo_mode; H.view_eyes = view_eyes; H.aa_pad = aa_pad ? 1 : 0;
     H.cam_dist = scn->cam.focal_distance;
     if (has_view) {
         H.off_view = off;
@@ -703,8 +733,8 @@ int ndt_b200_flatten_view(const void *scene_v, const void *kdtree_v, int width, 
             r = ndt_set_error(NDT_B200_E_ARG, "camera vectors not aimed (camera_aim must run first, ndt.c:1925)");
             goto done;
         }
-        if (stereo_mode != NDT_HIDEF_3D) v_scale(dx, width / (double)height, dx, np);   /* ndt.c:925-929 */
-        else v_scale(dx, width / (double)1080, dx, np);
+        if (stereo_mode != NDT_HIDEF_3D) v_scale(dx, out_width / (double)out_height, dx, np);   /* ndt.c:925-929 */
+        else v_scale(dx, out_width / (double)1080, dx, np);
         double sd = v_dist(orig, pos, np);             /* camera.c:567 */
         H.use_focal = sd > EPS;
         H.focal_scale = H.use_focal ? scn->cam.focal_distance / sd : 0.0;

@@ -244,6 +244,8 @@ struct WaveArgs {
     uint32_t *mb_bits;
     uint32_t mb_stride, mb_words, mb_shift;
     const void *leafrec;
+    const double *samples_xy; /* generation 0 from an explicit list of pixel-space positions (ip, jp) instead of the
+                                 tile's pixel grid: the sub-pixel samples of the recursive anti-aliasing */
 };
 
 /* the ray of slot r of this generation */
@@ -255,7 +257,9 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, int
     frac = 1.0;
     depth = sc.max_optic_depth;
     tx = ty = 0;
-    if (a.gen == 0) {
+    if (a.gen == 0 && a.samples_xy) {
+        if (active) primary_ray_at<NP>(sc, a.samples_xy[2 * (size_t)r], a.samples_xy[2 * (size_t)r + 1], o, v);
+    } else if (a.gen == 0) {
         const int blk = r >> 5;
         tx = (blk % a.bpr) * 8 + (lane & 7);
         ty = (blk / a.bpr) * 4 + (lane >> 3);
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(const Sce
             }
         }
         a.rec[a.start + r] = rec;
-        if (a.gen == 0) {
+        if (a.gen == 0 && !a.samples_xy) {
             const size_t p = (size_t)ty * a.tw + tx;
             if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
             if (a.out_id) a.out_id[p] = p_id;
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(const Sce
         z.h[0] = z.h[1] = z.h[2] = 0.0;
         z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
         a.rec[a.start + r] = z;
-        if (tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
+        if (!a.samples_xy && tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
             const size_t p = (size_t)ty * a.tw + tx;
             if (a.out_hit) a.out_hit[p] = 0;
             if (a.out_id) a.out_id[p] = -1;

@@ -71,7 +71,8 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
     unsigned long long rays_ref = 0, samples = 0, hits = 0, traced = 0;
     if (p < tw * th) {
         const int tx = p % tw, ty = p / tw;
-        const int slot = ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7);
+        /* bpr == 0: a sample list, record r belongs to sample r */
+        const int slot = bpr ? ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7) : p;
         RayRec r = rec[slot];
         const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
         const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
@@ -363,7 +364,8 @@ __global__ void k_anaglyph(const double *left, const double *right, int n, doubl
 
 static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                        void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
-                       void *d_obj_id, void *d_inv_depth, bool first, bool last);
+                       void *d_obj_id, void *d_inv_depth, bool first, bool last,
+                       const double *d_samples = NULL, int n_samples = 0);
 
 extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                                     void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
@@ -396,22 +398,27 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     return 0;
 }
 
+/* One pass over a tile of the frame, or -- d_samples != NULL -- over an explicit list of n_samples
+ * pixel-space positions (their colours go to d_rgba_f64[n_samples][4]) */
 static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                        void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
-                       void *d_obj_id, void *d_inv_depth, bool first, bool last)
+                       void *d_obj_id, void *d_inv_depth, bool first, bool last,
+                       const double *d_samples, int n_samples)
 {
+    if (d_samples) { x0 = 0; y0 = 0; tw = n_samples; th = 1; }
     if (!c->have_scene) return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_launch_tile before ndt_b200_upload");
     const ndt_flat_header &h = c->hdr;
-    if (tw <= 0 || th <= 0 || x0 < 0 || y0 < 0 || x0 + tw > h.width || y0 + th > h.height)
+    if (!d_samples && (tw <= 0 || th <= 0 || x0 < 0 || y0 < 0 || x0 + tw > h.width || y0 + th > h.height))
         return ndt_set_error(NDT_B200_E_ARG, "tile %dx%d+%d+%d outside the %dx%d frame", tw, th, x0, y0, h.width, h.height);
+    if (d_samples && n_samples <= 0) return ndt_set_error(NDT_B200_E_ARG, "empty sample list");
     CK(cudaSetDevice(c->device));
     const int np = h.npad;
     const bool cnt = (c->options & NDT_B200_OPT_COUNT_FLOPS) != 0;
-    const int bpr = (tw + 7) / 8, bprows = (th + 3) / 4;
-    const long long n0ll = (long long)bpr * bprows * 32;
+    const int bpr = d_samples ? 0 : (tw + 7) / 8, bprows = (th + 3) / 4;
+    const long long n0ll = d_samples ? (long long)n_samples : (long long)bpr * bprows * 32;
     if (n0ll > 0x3fffffff) return ndt_set_error(NDT_B200_E_ARG, "tile too large; render in smaller tiles");
     const int n0 = (int)n0ll;
-    const bool wave = !cnt && !(c->options & NDT_B200_OPT_FUSED);
+    const bool wave = d_samples || (!cnt && !(c->options & NDT_B200_OPT_FUSED));
     const int full_grid = wave ? trace_grid_for(c, np) : grid_for(c, np, cnt);
     int r = ensure_pools(c, n0, np, full_grid * BLOCK);
     if (r) return r;
@@ -447,6 +454,7 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
         a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
         a.mb_words = mb_words; a.mb_shift = mb_shift;
         a.leafrec = c->d_leafrec;
+        a.samples_xy = d_samples;
         while (count > 0) {
             if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
             gstart[ngen] = start; gcount[ngen] = count;
@@ -719,6 +727,250 @@ extern "C" int ndt_b200_fp64_peak(ndt_b200_ctx *c, int fused, double *gflops)
     double flops = (double)blocks * threads * (double)iters * 16.0;
     *gflops = flops / (best * 1e-3) / 1e9;
     return 0;
+}
+
+/* ---------------------------------------------------------------------------
+ * Recursive (Whitted) anti-aliasing: resample_pixel / recursive_resample (ndt.c:655-733) as a
+ * level-synchronous refinement.  A cell is one call of recursive_resample: a square of side `step`
+ * (in pixels of the (W+1) x (H+1) sample grid) with its four corner colours.  Level by level:
+ *   k_aa_level0     every pixel: image_avg_dbl_pixels4 of its corners (image.c:1175); pixels whose
+ *                   variance exceeds aa_diff/255 become level-0 cells and ask for their five samples
+ *   (wavefront over the sample list: launch_pass with d_samples)
+ *   k_aa_subdivide  every cell: the four sub-pixel averages and variances in the reference's operand
+ *                   order (ndt.c:684-702); sub-pixels over the threshold become cells of the next level
+ *                   (or, at the last level, are averaged in the CHILD's operand order: ndt.c:663-666)
+ *   k_aa_fold       deepest level first: res = average of the four sub-pixels -> the parent's slot
+ * The recursion of the reference is depth first, but every value only depends on its own subtree, so
+ * the order of evaluation is free; the order of OPERANDS inside every average is kept.
+ * ------------------------------------------------------------------------- */
+struct AaCell {
+    double x, y, step;
+    int32_t parent;          /* level 0: pixel index j*W+i; deeper: cell index in the previous level */
+    int32_t slot;            /* which sub-pixel of the parent this cell refines */
+    double corner[4][4];     /* p1..p4 RGBA, recursive_resample's argument order */
+    double sp[4][4];         /* sp1..sp4 (ndt.c:680): sub-pixel colours */
+};
+
+__device__ __forceinline__ void aa_avg4(const double *p1, const double *p2, const double *p3, const double *p4,
+                                        double *avg, double *var)          /* image.c:1175-1197 */
+{
+    for (int k = 0; k < 4; ++k) avg[k] = (p1[k] + p2[k] + p3[k] + p4[k]) / 4;
+    if (var) {
+        double v = 0;
+        for (int k = 0; k < 4; ++k)
+            v += fabs(avg[k] - p1[k]) + fabs(avg[k] - p2[k]) + fabs(avg[k] - p3[k]) + fabs(avg[k] - p4[k]);
+        *var = v;
+    }
+}
+
+/* the five samples recursive_resample renders for a cell: centre, top middle, left, right, bottom (ndt.c:668-676) */
+__device__ __forceinline__ void aa_emit_samples(double *xy, double x, double y, double step)
+{
+    const double hs = step / 2;
+    xy[0] = x + hs;   xy[1] = y + hs;
+    xy[2] = x + hs;   xy[3] = y;
+    xy[4] = x;        xy[5] = y + hs;
+    xy[6] = x + step; xy[7] = y + hs;
+    xy[8] = x + hs;   xy[9] = y + step;
+}
+
+__global__ void k_aa_level0(const double *img, int W, int H, double thr, int subdivide,
+                            double *fin, AaCell *cells, int *n_cells, double *samples_xy,
+                            unsigned long long *resampled)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int i = p % W, j = p / W;
+    const double *p1 = img + 4 * ((size_t)(W + 1) * j + i), *p2 = p1 + 4;
+    const double *p3 = img + 4 * ((size_t)(W + 1) * (j + 1) + i), *p4 = p3 + 4;
+    double avg[4], var;
+    aa_avg4(p1, p2, p3, p4, avg, &var);                 /* resample_pixel, ndt.c:719-723 */
+    for (int k = 0; k < 4; ++k) fin[4 * (size_t)p + k] = avg[k];
+    if (!(var > thr)) return;
+    atomicAdd(resampled, 1ull);
+    if (!subdivide) return;                             /* recursive_resample returns the same average (ndt.c:663-666) */
+    const int c = atomicAdd(n_cells, 1);
+    AaCell *cell = cells + c;
+    cell->x = i; cell->y = j; cell->step = 1.0;
+    cell->parent = p; cell->slot = 0;
+    for (int k = 0; k < 4; ++k) {
+        cell->corner[0][k] = p1[k]; cell->corner[1][k] = p2[k];
+        cell->corner[2][k] = p3[k]; cell->corner[3][k] = p4[k];
+    }
+    aa_emit_samples(samples_xy + 10 * (size_t)c, i, j, 1.0);
+}
+
+__global__ void k_aa_subdivide(AaCell *cells, int n, const double *samp, double thr, int next_terminal,
+                               AaCell *next, int *n_next, double *next_xy)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    AaCell *cell = cells + c;
+    const double *p1 = cell->corner[0], *p2 = cell->corner[1], *p3 = cell->corner[2], *p4 = cell->corner[3];
+    const double *p5 = samp + 20 * (size_t)c, *p6 = p5 + 4, *p7 = p5 + 8, *p8 = p5 + 12, *p9 = p5 + 16;
+    const double x = cell->x, y = cell->y, hs = cell->step / 2;
+    /* operands of the sub-pixel average (ndt.c:685,690,695,700) and of the recursive call (:687,692,697,702) */
+    const double *av[4][4] = { { p1, p6, p7, p5 }, { p2, p6, p8, p5 }, { p3, p9, p7, p5 }, { p4, p9, p8, p5 } };
+    const double *rc[4][4] = { { p1, p6, p7, p5 }, { p6, p2, p5, p8 }, { p7, p5, p3, p9 }, { p5, p8, p9, p4 } };
+    const double ox[4] = { x, x + hs, x, x + hs }, oy[4] = { y, y, y + hs, y + hs };
+    for (int k = 0; k < 4; ++k) {
+        double var;
+        aa_avg4(av[k][0], av[k][1], av[k][2], av[k][3], cell->sp[k], &var);
+        if (!(var > thr)) continue;
+        if (next_terminal) {
+            /* the recursive call returns at once with the average in ITS operand order (ndt.c:663-666) */
+            aa_avg4(rc[k][0], rc[k][1], rc[k][2], rc[k][3], cell->sp[k], NULL);
+            continue;
+        }
+        const int d = atomicAdd(n_next, 1);
+        AaCell *ch = next + d;
+        ch->x = ox[k]; ch->y = oy[k]; ch->step = hs;
+        ch->parent = c; ch->slot = k;
+        for (int q = 0; q < 4; ++q)
+            for (int e = 0; e < 4; ++e) ch->corner[q][e] = rc[k][q][e];
+        aa_emit_samples(next_xy + 10 * (size_t)d, ox[k], oy[k], hs);
+    }
+}
+
+__global__ void k_aa_fold(const AaCell *cells, int n, AaCell *parents, double *fin)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const AaCell *cell = cells + c;
+    double res[4];
+    aa_avg4(cell->sp[0], cell->sp[1], cell->sp[2], cell->sp[3], res, NULL);     /* ndt.c:704 */
+    double *dst = parents ? parents[cell->parent].sp[cell->slot] : fin + 4 * (size_t)cell->parent;
+    for (int k = 0; k < 4; ++k) dst[k] = res[k];
+}
+
+/* dbl_image_set_pixel into the 8-bit actual_img (ndt.c:777, image.c:126-146, image.h:36-39) */
+__global__ void k_aa_store(const double *fin, int n, uint8_t *u8)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double *f = fin + 4 * (size_t)p;
+    reinterpret_cast<uchar4 *>(u8)[p] = make_uchar4(d2c(f[0]), d2c(f[1]), d2c(f[2]), d2c(f[3]));
+}
+
+/* "simply copy img to actual_img" (ndt.c:1089-1100) when aa_depth < 0 or aa_diff >= 256 */
+__global__ void k_aa_copy(const double *img, int W, int H, double *fin)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int i = p % W, j = p / W;
+    const double *s = img + 4 * ((size_t)(W + 1) * j + i);
+    for (int k = 0; k < 4; ++k) fin[4 * (size_t)p + k] = s[k];
+}
+
+static int aa_terminal(int aa_depth, double step)      /* ndt.c:663 */
+{
+    return aa_depth <= 0 || step < 1.0 / (2 << (aa_depth - 1));
+}
+
+extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
+                                  uint8_t *rgba_u8, double *rgba_f64, uint64_t *pixels_resampled,
+                                  ndt_b200_stats *stats)
+{
+    if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    if (!c->have_scene) return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_render_aa before ndt_b200_upload");
+    if (!c->hdr.aa_pad)
+        return ndt_set_error(NDT_B200_E_STATE, "ndt_b200_render_aa needs a scene from ndt_b200_flatten_aa (the (W+1) x (H+1) sample grid)");
+    if (aa_depth > 30) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "aa_depth %d: 2 << (aa_depth-1) overflows (ndt.c:663)", aa_depth);
+    CK(cudaSetDevice(c->device));
+    const int W = c->hdr.width - 1, H = c->hdr.height - 1;
+    const size_t px = (size_t)W * H, gpx = (size_t)(W + 1) * (H + 1);
+    cudaStream_t st = c->stream;
+    ndt_b200_stats acc;
+    memset(&acc, 0, sizeof acc);
+    int r = 0;
+    double *d_img = NULL, *d_fin = NULL;
+    uint8_t *d_u8 = NULL;
+    int *d_cnt = NULL;
+    unsigned long long *d_res = NULL;
+    AaCell *lvl_cells[64];
+    int lvl_n[64], nlvl = 0;
+    double *d_xy = NULL, *d_samp = NULL;
+    memset(lvl_cells, 0, sizeof lvl_cells);
+#define AA_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        r = ndt_set_error(NDT_B200_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); goto aa_done; } } while (0)
+    AA_CK(cudaMalloc(&d_img, gpx * 32));
+    AA_CK(cudaMalloc(&d_fin, px * 32));
+    AA_CK(cudaMalloc(&d_u8, px * 4));
+    AA_CK(cudaMalloc(&d_cnt, sizeof(int)));
+    AA_CK(cudaMalloc(&d_res, sizeof(unsigned long long)));
+    AA_CK(cudaMemsetAsync(d_res, 0, sizeof(unsigned long long), st));
+
+    /* the initial image: one sample per corner (render_lines_thread with width+1, height+1) */
+    if ((r = ndt_b200_launch_tile(c, 0, 0, W + 1, H + 1, d_img, NULL, NULL, NULL, NULL))) goto aa_done;
+    if ((r = ndt_b200_sync(c))) goto aa_done;
+    stats_add(&acc, &c->last);
+
+    if (!(aa_depth >= 0 && aa_diff < 256)) {
+        k_aa_copy<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(d_img, W, H, d_fin);
+    } else {
+        const double thr = aa_diff / 255.0;
+        double step = 1.0;
+        AA_CK(cudaMalloc(&lvl_cells[0], (px ? px : 1) * sizeof(AaCell)));
+        AA_CK(cudaMalloc(&d_xy, (px ? px : 1) * 10 * sizeof(double)));
+        AA_CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+        k_aa_level0<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(d_img, W, H, thr, !aa_terminal(aa_depth, step), d_fin,
+                                                                 lvl_cells[0], d_cnt, d_xy, d_res);
+        AA_CK(cudaGetLastError());
+        int n = 0;
+        AA_CK(cudaMemcpyAsync(&n, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        AA_CK(cudaStreamSynchronize(st));
+        while (n > 0) {
+            if (nlvl >= 62) { r = ndt_set_error(NDT_B200_E_OVERFLOW, "more than 62 anti-aliasing levels"); goto aa_done; }
+            lvl_n[nlvl] = n;
+            if ((size_t)n * 5 > 0x3ffffff0u) { r = ndt_set_error(NDT_B200_E_OVERFLOW, "too many anti-aliasing samples in one level"); goto aa_done; }
+            /* this level's samples: one wavefront over the list */
+            cudaFree(d_samp); d_samp = NULL;
+            AA_CK(cudaMalloc(&d_samp, (size_t)n * 5 * 32));
+            c->sc.eye_override = 0;
+            if ((r = launch_pass(c, 0, 0, 0, 0, d_samp, NULL, NULL, NULL, NULL, true, true, d_xy, n * 5))) goto aa_done;
+            if ((r = ndt_b200_sync(c))) goto aa_done;
+            stats_add(&acc, &c->last);
+            const int next_terminal = aa_terminal(aa_depth, step / 2);
+            double *d_xy_next = NULL;
+            if (!next_terminal) {
+                AA_CK(cudaMalloc(&lvl_cells[nlvl + 1], (size_t)n * 4 * sizeof(AaCell)));
+                AA_CK(cudaMalloc(&d_xy_next, (size_t)n * 4 * 10 * sizeof(double)));
+            }
+            AA_CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+            k_aa_subdivide<<<(n + 127) / 128, 128, 0, st>>>(lvl_cells[nlvl], n, d_samp, thr, next_terminal,
+                                                            lvl_cells[nlvl + 1], d_cnt, d_xy_next);
+            AA_CK(cudaGetLastError());
+            int nn = 0;
+            AA_CK(cudaMemcpyAsync(&nn, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+            AA_CK(cudaStreamSynchronize(st));
+            cudaFree(d_xy); d_xy = d_xy_next;
+            ++nlvl;
+            step /= 2;
+            n = nn;
+        }
+        for (int l = nlvl - 1; l >= 0; --l)
+            k_aa_fold<<<(lvl_n[l] + 127) / 128, 128, 0, st>>>(lvl_cells[l], lvl_n[l], l ? lvl_cells[l - 1] : NULL, d_fin);
+    }
+    k_aa_store<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(d_fin, (int)px, d_u8);
+    AA_CK(cudaGetLastError());
+    if (rgba_u8) AA_CK(cudaMemcpyAsync(rgba_u8, d_u8, px * 4, cudaMemcpyDeviceToHost, st));
+    if (rgba_f64) AA_CK(cudaMemcpyAsync(rgba_f64, d_fin, px * 32, cudaMemcpyDeviceToHost, st));
+    {
+        unsigned long long res = 0;
+        AA_CK(cudaMemcpyAsync(&res, d_res, sizeof res, cudaMemcpyDeviceToHost, st));
+        AA_CK(cudaStreamSynchronize(st));
+        if (pixels_resampled) *pixels_resampled = res;
+    }
+    acc.launches += 2 + (uint64_t)nlvl * 2;
+    c->last = acc;
+    if (stats) *stats = acc;
+aa_done:
+#undef AA_CK
+    cudaStreamSynchronize(st);
+    cudaFree(d_img); cudaFree(d_fin); cudaFree(d_u8); cudaFree(d_cnt); cudaFree(d_res);
+    cudaFree(d_xy); cudaFree(d_samp);
+    for (int l = 0; l < 64; ++l) cudaFree(lvl_cells[l]);
+    return r;
 }
 
 /* drop-in for render_image (ndt.c:900) */

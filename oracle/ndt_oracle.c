@@ -1040,6 +1040,153 @@ int ndo_render(const void *blob, int x0, int y0, int tw, int th, int threads,
     return 0;
 }
 
+/* ---- recursive anti-aliasing: resample_pixel / recursive_resample, ndt.c:655-733 ------------------- */
+typedef struct { double c[4]; } px4;
+
+static void avg4(const px4 *p1, const px4 *p2, const px4 *p3, const px4 *p4, px4 *avg, double *var)
+{   /* image_avg_dbl_pixels4, image.c:1175-1197 */
+    for (int k = 0; k < 4; ++k) avg->c[k] = (p1->c[k] + p2->c[k] + p3->c[k] + p4->c[k]) / 4;
+    if (var) {
+        double v = 0;
+        for (int k = 0; k < 4; ++k)
+            v += fabs(avg->c[k] - p1->c[k]) + fabs(avg->c[k] - p2->c[k]) +
+                 fabs(avg->c[k] - p3->c[k]) + fabs(avg->c[k] - p4->c[k]);
+        *var = v;
+    }
+}
+
+typedef struct {
+    view *w; unsigned char *mask; raycnt rc; uint64_t rays_ref, samples;
+    int aa_diff, aa_depth;
+} aa_ctx;
+
+/* render_pixel at a fractional pixel position (MONO, CAMERA_NORMAL): ndt.c:628-650 */
+static void aa_sample(aa_ctx *A, double ip, double jp, px4 *out)
+{
+    view *w = A->w;
+    const int np = w->np;
+    const double *cpos = w->cam, *corig = w->cam + np, *cdx = w->cam + 2 * np, *cdy = w->cam + 3 * np;
+    double x = ip / (double)w->h->width - 0.5;
+    double y = -(jp / (double)w->h->height - 0.5);
+    double pixel[MAXD], tmp[MAXD], look[MAXD];
+    vcopy(pixel, corig, np);
+    vscale(cdx, x, tmp, np); vadd(pixel, tmp, pixel, np);
+    vscale(cdy, y, tmp, np); vadd(pixel, tmp, pixel, np);
+    if (w->h->use_focal) {
+        vsub(pixel, cpos, tmp, np);
+        vscale(tmp, w->h->focal_scale, tmp, np);
+        vadd(cpos, tmp, pixel, np);
+    }
+    vsub(pixel, cpos, look, np);
+    vunit(look, np);
+    raycnt rc = {0, 0, 0};
+    double l[4];
+    int ph = 0, pid = -1; double pd = -1;
+    ray_color(w, A->mask, &rc, cpos, look, l, 1.0, w->h->max_optic_depth, 1, &ph, &pid, &pd);
+    int ns = replay_samples(l, out->c);
+    A->rc.primary += rc.primary; A->rc.bounce += rc.bounce; A->rc.shadow += rc.shadow;
+    A->rays_ref += (rc.primary + rc.bounce + rc.shadow) * (uint64_t)ns; A->samples += (uint64_t)ns;
+}
+
+static void aa_recurse(aa_ctx *A, double x, double y, double step,
+                       const px4 *p1, const px4 *p2, const px4 *p3, const px4 *p4, px4 *res)
+{
+    if (A->aa_depth <= 0 || step < 1.0 / (2 << (A->aa_depth - 1))) {      /* ndt.c:663-666 */
+        avg4(p1, p2, p3, p4, res, NULL);
+        return;
+    }
+    double hs = step / 2;
+    px4 p5, p6, p7, p8, p9;
+    aa_sample(A, x + hs, y + hs, &p5);
+    aa_sample(A, x + hs, y, &p6);
+    aa_sample(A, x, y + hs, &p7);
+    aa_sample(A, x + step, y + hs, &p8);
+    aa_sample(A, x + hs, y + step, &p9);
+    px4 sp1, sp2, sp3, sp4;
+    double var1 = 0, var2 = 0, var3 = 0, var4 = 0;
+    double threshold = A->aa_diff / 255.0;
+    avg4(p1, &p6, &p7, &p5, &sp1, &var1);
+    if (var1 > threshold) aa_recurse(A, x, y, hs, p1, &p6, &p7, &p5, &sp1);
+    avg4(p2, &p6, &p8, &p5, &sp2, &var2);
+    if (var2 > threshold) aa_recurse(A, x + hs, y, hs, &p6, p2, &p5, &p8, &sp2);
+    avg4(p3, &p9, &p7, &p5, &sp3, &var3);
+    if (var3 > threshold) aa_recurse(A, x, y + hs, hs, &p7, &p5, p3, &p9, &sp3);
+    avg4(p4, &p9, &p8, &p5, &sp4, &var4);
+    if (var4 > threshold) aa_recurse(A, x + hs, y + hs, hs, &p5, &p8, &p9, p4, &sp4);
+    avg4(&sp1, &sp2, &sp3, &sp4, res, NULL);
+}
+
+typedef struct {
+    const void *blob; const double *img; int W, H, row0, rows_step, aa_diff, aa_depth;
+    uint8_t *u8; double *f64; uint64_t st[6];
+} aa_job;
+
+static void *aa_rows(void *arg)
+{
+    aa_job *J = arg;
+    view Wv;
+    view_init(&Wv, J->blob);
+    aa_ctx A;
+    memset(&A, 0, sizeof A);
+    A.w = &Wv; A.aa_diff = J->aa_diff; A.aa_depth = J->aa_depth;
+    A.mask = malloc((size_t)(Wv.h->n_items ? Wv.h->n_items : 1));
+    const int W = J->W, H = J->H;
+    for (int j = J->row0; j < H; j += J->rows_step)
+        for (int i = 0; i < W; ++i) {
+            const px4 *p1 = (const px4 *)(J->img + 4 * ((size_t)(W + 1) * j + i)), *p2 = p1 + 1;
+            const px4 *p3 = (const px4 *)(J->img + 4 * ((size_t)(W + 1) * (j + 1) + i)), *p4 = p3 + 1;
+            px4 clr;
+            if (J->aa_depth >= 0 && J->aa_diff < 256) {
+                double var = 0.0;
+                avg4(p1, p2, p3, p4, &clr, &var);                 /* resample_pixel, ndt.c:709-733 */
+                if (var > J->aa_diff / 255.0) {
+                    J->st[5]++;
+                    aa_recurse(&A, i, j, 1.0, p1, p2, p3, p4, &clr);
+                }
+            } else {
+                clr = *p1;                                         /* ndt.c:1089-1100 */
+            }
+            size_t p = (size_t)j * W + i;
+            if (J->f64) memcpy(J->f64 + 4 * p, clr.c, 32);
+            if (J->u8) for (int k = 0; k < 4; ++k) J->u8[4 * p + k] = d2c(clr.c[k]);
+        }
+    J->st[0] = A.rc.primary; J->st[1] = A.rc.bounce; J->st[2] = A.rc.shadow; J->st[3] = A.rays_ref; J->st[4] = A.samples;
+    free(A.mask);
+    return NULL;
+}
+
+/* render_image with recursive_aa set (ndt.c:921-926, 1039-1100) over a scene from ndt_b200_flatten_aa.
+ * u8: W x H RGBA as stored in the 8-bit actual_img; f64: the colours before quantisation.
+ * stats[6]: rays_primary, rays_bounce, rays_shadow, rays_ref, samples, pixels resampled */
+int ndo_render_aa(const void *blob, int threads, int aa_diff, int aa_depth, uint8_t *u8, double *f64, uint64_t *stats)
+{
+    const ndt_flat_header *h = blob;
+    if (!h || h->magic != NDT_FLAT_MAGIC || h->version != NDT_FLAT_VERSION || !h->aa_pad) return -1;
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    const int W = h->width - 1, H = h->height - 1;
+    double *img = malloc((size_t)(W + 1) * (H + 1) * 32);
+    if (!img) return -2;
+    uint64_t st0[5] = {0};
+    render_pass(blob, 0, 0, W + 1, H + 1, threads, 0, img, NULL, NULL, NULL, NULL, st0);
+    aa_job *jobs = calloc((size_t)threads, sizeof *jobs);
+    pthread_t *thr = calloc((size_t)threads, sizeof *thr);
+    for (int t = 0; t < threads; ++t) {
+        aa_job *J = &jobs[t];
+        J->blob = blob; J->img = img; J->W = W; J->H = H; J->row0 = t; J->rows_step = threads;
+        J->aa_diff = aa_diff; J->aa_depth = aa_depth; J->u8 = u8; J->f64 = f64;
+        if (threads > 1) pthread_create(&thr[t], NULL, aa_rows, J);
+        else aa_rows(J);
+    }
+    if (stats) { memset(stats, 0, 6 * sizeof *stats); for (int k = 0; k < 5; ++k) stats[k] = st0[k]; }
+    for (int t = 0; t < threads; ++t) {
+        if (threads > 1) pthread_join(thr[t], NULL);
+        if (stats) for (int k = 0; k < 6; ++k) stats[k] += jobs[t].st[k];
+    }
+    free(jobs); free(thr); free(img);
+    return 0;
+}
+
 /* one nearest-hit query, for the per-primitive known-answer tests */
 int ndo_trace(const void *blob, const double *o_in, const double *v_in, double dist_limit,
               double *hit_out, double *normal_out, int *obj_id)

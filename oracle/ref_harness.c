@@ -220,6 +220,36 @@ int refh_num_items(void) { return g_nflat; }
 void *refh_object_get_bounds_ptr(void) { return (void *)object_get_bounds; }
 void refh_set_specular(int on) { specular_enabled = on; }
 
+/* render_image with the global recursive_aa set (-w / -a, ndt.c:1455-1466): returns the 8-bit
+ * actual_img (ndt.c:940-942) the reference saves last */
+extern int recursive_aa;
+int refh_render_aa(int w, int h, int threads, int max_optic_depth, int aa_diff, int aa_depth,
+                   unsigned char *rgba_u8, double *seconds)
+{
+    if (!g_frame_open)
+        return -1;
+    if (g_dirx_scaled)
+        return -2;
+    struct timespec a, b;
+    hush(1);
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    recursive_aa = 1;
+    render_image(&g_scn, "oracle", NULL, w, h, 1, REF_MONO, threads, aa_diff, aa_depth, max_optic_depth, NULL, NULL);
+    recursive_aa = 0;
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    hush(0);
+    g_dirx_scaled = 1;
+    if (seconds)
+        *seconds = (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+    const unsigned char *px; int cw, ch, pw;
+    if (!ref_shim_captured(&px, &cw, &ch, &pw) || cw != w || ch != h || pw != 4)
+        return -3;
+    if (rgba_u8)
+        memcpy(rgba_u8, px, (size_t)w * h * 4);
+    ref_shim_drop();
+    return 0;
+}
+
 void *refh_rotate2_ptr(void) { return (void *)vectNd_rotate2; }
 
 /* what main() does for -V / -P before camera_aim (ndt.c:1915-1925): camera type and fields of view */

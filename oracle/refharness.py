@@ -50,6 +50,7 @@ class RefHarness:
         L.refh_object_get_bounds_ptr.restype = C.c_void_p
         L.refh_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.refh_render_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.refh_render_aa.argtypes = [C.c_int] * 6 + [C.c_void_p, C.POINTER(C.c_double)]
         L.refh_set_camera.argtypes = [C.c_int, C.c_double, C.c_double]
         L.refh_rotate2_ptr.restype = C.c_void_p
         L.refh_primary.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -140,6 +141,16 @@ class RefHarness:
         r = self.lib.refh_render_ex(w, h, threads, max_optic_depth, stereo, out.ctypes.data, C.byref(sec))
         if r != 0:
             raise RuntimeError(f"refh_render_ex -> {r}")
+        return out, sec.value
+
+    def render_aa(self, w, h, aa_diff=20, aa_depth=4, threads=None, max_optic_depth=128):
+        """8-bit RGBA [h, w, 4]: render_image with recursive_aa set (-w / -a), i.e. Whitted resampling."""
+        threads = threads or os.cpu_count()
+        out = np.empty((h, w, 4), dtype=np.uint8)
+        sec = C.c_double(0)
+        r = self.lib.refh_render_aa(w, h, threads, max_optic_depth, aa_diff, aa_depth, out.ctypes.data, C.byref(sec))
+        if r != 0:
+            raise RuntimeError(f"refh_render_aa -> {r}")
         return out, sec.value
 
     def set_camera(self, cam_type, h_fov=0.0, v_fov=0.0):

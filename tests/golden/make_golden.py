@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 import ndt_b200  # noqa: E402
 from oracle.refharness import RefHarness, rgba_f64_to_u8  # noqa: E402
-from scenes import CASES, H_FOV, V_FOV  # noqa: E402
+from scenes import AA_CASES, AA_PARAMS, CASES, H_FOV, V_FOV  # noqa: E402
 
 
 def sha(a):
@@ -131,6 +131,23 @@ def main():
         }
         print(c.key, "flat", len(flat), "hit px", int(hit.sum()), "kats", len(kats),
               "found", sum(k["found"] for k in kats), flush=True)
+    # recursive anti-aliasing: the reference's 8-bit actual_img per (aa_diff, aa_depth)
+    for c in AA_CASES:
+        R.open_scene(c.scene)
+        frames = R.scene_frames(c.dims, c.cfg) if c.scene else 300
+        if frames <= 0:
+            frames = 300
+        shas = {}
+        for diff, depth in AA_PARAMS:
+            R.begin_frame(c.dims, c.frame, frames, c.cfg)
+            flat = ndt_b200.flatten_aa(R.scene_ptr, R.kdtree_ptr, c.w, c.h, 128, 1, R.get_bounds_ptr)
+            u8, _ = R.render_aa(c.w, c.h, diff, depth)
+            R.end_frame()
+            shas[f"{diff},{depth}"] = sha(u8)
+        flat.save(os.path.join(HERE, c.key + ".ndsf.gz"))
+        out[c.key] = {"scene": c.scene, "dims": c.dims, "cfg": c.cfg, "frame": c.frame, "w": c.w, "h": c.h,
+                      "aa": True, "flat_bytes": len(flat), "sha_u8_by_params": shas}
+        print(c.key, "flat", len(flat), flush=True)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 

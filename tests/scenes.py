@@ -44,3 +44,14 @@ VIEW_CASES = [
 BASE_CASES = list(CASES)
 CASES = CASES + VIEW_CASES
 BY_KEY = {c.key: c for c in CASES}
+
+# recursive (Whitted) anti-aliasing, -w / -a: (key, scene, dims, cfg, frame, w, h) and the
+# (aa_diff, aa_depth) pairs rendered for each: the default -a, the two -q presets that refine, and the two
+# that do not (ndt.c:1589-1624, 1411-1412)
+AaCase = namedtuple("AaCase", "key scene dims cfg frame w h")
+AA_CASES = [
+    AaCase("aa_default4d", None, 4, None, 0, 96, 54),
+    AaCase("aa_hcube5d", "hypercube", 5, "hcube", 3, 64, 36),
+    AaCase("aa_mixed7d", "mixed10d", 7, None, 5, 64, 36),
+]
+AA_PARAMS = [(20, 4), (1, 2), (5, 0), (255, 0), (20, -1)]

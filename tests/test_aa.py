@@ -1,0 +1,95 @@
+"""Recursive (Whitted) anti-aliasing, render_image with recursive_aa set (ndt.c:655-733, 1039-1100;
+SURVEY 8f rank 2).  The reference stores the result in the 8-bit actual_img, so the pin is on u8.
+  CPU: the oracle's ndo_render_aa against the committed digests of the reference and, where oracle/_ref
+       is present, against the live reference;
+  GPU: ndt_b200_render_aa (level-synchronous refinement, one wavefront per level) against the oracle."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import ndt_b200
+from conftest import load_flat
+from scenes import AA_CASES, AA_PARAMS
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def oracle_aa(L, flat, diff, depth, want_f64=False):
+    L.ndo_render_aa.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    w, h = flat.header.width - 1, flat.header.height - 1
+    u8 = np.zeros((h, w, 4), np.uint8)
+    f64 = np.zeros((h, w, 4), np.float64) if want_f64 else None
+    st = (C.c_uint64 * 6)()
+    assert L.ndo_render_aa(flat.blob, os.cpu_count(), diff, depth, u8.ctypes.data,
+                           f64.ctypes.data if want_f64 else None, st) == 0
+    return u8, f64, list(st)
+
+
+@pytest.mark.parametrize("case", AA_CASES, ids=[c.key for c in AA_CASES])
+def test_oracle_aa_matches_reference_digests(case, golden, oracle_lib):
+    g = golden[case.key]
+    flat = load_flat(case.key)
+    assert flat.header.aa_pad == 1 and flat.header.width == case.w + 1 and len(flat) == g["flat_bytes"]
+    for diff, depth in AA_PARAMS:
+        u8, _, st = oracle_aa(oracle_lib, flat, diff, depth)
+        assert sha(u8) == g["sha_u8_by_params"][f"{diff},{depth}"], (diff, depth)
+        if depth < 0:
+            assert st[5] == 0          # "simply copy img to actual_img" (ndt.c:1089)
+
+
+@pytest.mark.parametrize("case", AA_CASES, ids=[c.key for c in AA_CASES])
+def test_oracle_aa_matches_live_reference(case, ref, oracle_lib):
+    ref.open_scene(case.scene)
+    frames = ref.scene_frames(case.dims, case.cfg) if case.scene else 300
+    for diff, depth in AA_PARAMS[:3]:
+        ref.begin_frame(case.dims, case.frame, frames if frames > 0 else 300, case.cfg)
+        try:
+            flat = ndt_b200.flatten_aa(ref.scene_ptr, ref.kdtree_ptr, case.w, case.h, 128, 1, ref.get_bounds_ptr)
+            want, _ = ref.render_aa(case.w, case.h, diff, depth)
+        finally:
+            ref.end_frame()
+        assert flat.blob == load_flat(case.key).blob
+        u8, _, _ = oracle_aa(oracle_lib, flat, diff, depth)
+        assert np.array_equal(u8, want), (diff, depth, int((u8 != want).sum()))
+
+
+def test_aa_scene_is_refused_by_the_plain_entry_points_and_vice_versa():
+    L = ndt_b200.lib()
+    flat = load_flat("config1_default4d")
+    assert flat.header.aa_pad == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", AA_CASES, ids=[c.key for c in AA_CASES])
+def test_cuda_aa_matches_oracle(case, oracle_lib):
+    flat = load_flat(case.key)
+    with ndt_b200.Context(0) as ctx:
+        ctx.upload(flat)
+        for diff, depth in AA_PARAMS:
+            want, want_f64, st = oracle_aa(oracle_lib, flat, diff, depth, want_f64=True)
+            got, got_f64, resampled, stats = ctx.render_aa(diff, depth, want_f64=True)
+            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            ok = float((d <= 1).mean())
+            print(f"\n{case.key} aa_diff={diff} aa_depth={depth}: u8 identical {float((d == 0).mean())*100:.3f}%, "
+                  f"within 1 LSB {ok*100:.3f}%, resampled {resampled} (oracle {st[5]}), "
+                  f"max |d f64| {np.abs(got_f64 - want_f64).max():.3g}, rays {stats.rays_unique}")
+            assert ok >= 0.999
+            # which pixels are refined depends on colours that differ in the last bits (CUDA libm): allow a few
+            assert abs(int(resampled) - int(st[5])) <= max(2, 0.002 * st[5])
+            uniq = st[0] + st[1] + st[2]
+            assert abs(int(stats.rays_unique) - uniq) <= max(8, 0.005 * uniq)
+
+
+@pytest.mark.gpu
+def test_cuda_aa_needs_an_aa_scene():
+    flat = load_flat("config1_default4d")
+    with ndt_b200.Context(0) as ctx:
+        ctx.upload(flat)
+        with pytest.raises(ndt_b200.NdtB200Error) as e:
+            ctx.render_aa(20, 4)
+        assert e.value.code == -4 or e.value.code < 0
