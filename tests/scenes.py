@@ -52,6 +52,6 @@ AaCase = namedtuple("AaCase", "key scene dims cfg frame w h")
 AA_CASES = [
     AaCase("aa_default4d", None, 4, None, 0, 96, 54),
     AaCase("aa_hcube5d", "hypercube", 5, "hcube", 3, 64, 36),
-    AaCase("aa_mixed7d", "mixed10d", 7, None, 5, 64, 36),
+    AaCase("aa_mixed7d", "mixed10d", 7, None, 5, 40, 24),
 ]
 AA_PARAMS = [(20, 4), (1, 2), (5, 0), (255, 0), (20, -1)]

@@ -46,7 +46,8 @@ def test_oracle_aa_matches_reference_digests(case, golden, oracle_lib):
 def test_oracle_aa_matches_live_reference(case, ref, oracle_lib):
     ref.open_scene(case.scene)
     frames = ref.scene_frames(case.dims, case.cfg) if case.scene else 300
-    for diff, depth in AA_PARAMS[:3]:
+    # the reference refines mixed7d almost everywhere (minutes at depth 4): its deep levels are pinned by the digests
+    for diff, depth in (((5, 0),) if case.key == "aa_mixed7d" else ((20, 4), (5, 0))):
         ref.begin_frame(case.dims, case.frame, frames if frames > 0 else 300, case.cfg)
         try:
             flat = ndt_b200.flatten_aa(ref.scene_ptr, ref.kdtree_ptr, case.w, case.h, 128, 1, ref.get_bounds_ptr)
