@@ -159,6 +159,15 @@ int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_a
                           int aa_depth, int max_optic_depth, int specular,
                           void *img_copy, void *depth_copy);
 
+/* The same call when the reference's global recursive_aa (ndt.c:44, set by -w / -a) is non-zero:
+ * ndt_b200_flatten_aa + ndt_b200_render_aa; img_copy receives the 8-bit actual_img (ndt.c:1124-1127).
+ * MONO only. */
+int ndt_b200_render_image_aa(void *scene, const void *kdtree, const ndt_b200_host_api *host,
+                             char *name, char *depth_name, int width, int height,
+                             int samples, int stereo_mode, int threads, int aa_diff,
+                             int aa_depth, int max_optic_depth, int specular,
+                             void *img_copy, void *depth_copy);
+
 /* Page-locked host memory (cudaMallocHost) for render_tile outputs and flat
  * scenes; plain malloc'ed buffers work too, only slower to copy. */
 void *ndt_b200_host_alloc(size_t bytes);

@@ -24,6 +24,7 @@
 
 extern char kdtree[];                    /* kd_tree_t kdtree, ndt.c:68 */
 extern int specular_enabled;             /* ndt.c:41 */
+extern int recursive_aa;                 /* ndt.c:44 (-w / -a) */
 int object_get_bounds(void *obj);        /* object.c:582 */
 int vectNd_rotate2(void *v, void *center, void *v1, void *v2, double angle, void *res);   /* vectNd.c:271 */
 int ndt_ref_main(int argc, char **argv); /* ndt.c:1390 compiled with -Dmain=ndt_ref_main */
@@ -43,9 +44,9 @@ int render_image(void *scn, char *name, char *depth_name, int width, int height,
     ndtabi_image local;
     memset(&local, 0, sizeof local);
     ndtabi_image *img = img_copy ? (ndtabi_image *)img_copy : &local;
-    int rc = ndt_b200_render_image(scn, kdtree, &host, name, depth_name, width, height, samples, mode,
-                                   threads, aa_diff, aa_depth, max_optic_depth, specular_enabled,
-                                   img, depth_copy);
+    int rc = (recursive_aa ? ndt_b200_render_image_aa : ndt_b200_render_image)(
+        scn, kdtree, &host, name, depth_name, width, height, samples, mode,
+        threads, aa_diff, aa_depth, max_optic_depth, specular_enabled, img, depth_copy);
     if (rc < 0) {
         fprintf(stderr, "ndt_b200: %s\n", ndt_b200_last_error());
         exit(1);                         /* the host application decides; there is no CPU fallback */
@@ -59,10 +60,14 @@ int render_image(void *scn, char *name, char *depth_name, int width, int height,
         FILE *f = fopen(path, "wb");
         if (f) {
             fprintf(f, "P6\n%d %d\n255\n", width, height);
-            const double *px = (const double *)img->pixels;
-            for (size_t i = 0; i < (size_t)width * height; ++i) {
-                unsigned char rgb[3] = { d2c(px[4 * i]), d2c(px[4 * i + 1]), d2c(px[4 * i + 2]) };
-                fwrite(rgb, 1, 3, f);
+            if (img->pixel_width == 4) {         /* the anti-aliased frame is already 8-bit RGBA */
+                for (size_t i = 0; i < (size_t)width * height; ++i) fwrite(img->pixels + 4 * i, 1, 3, f);
+            } else {
+                const double *px = (const double *)img->pixels;
+                for (size_t i = 0; i < (size_t)width * height; ++i) {
+                    unsigned char rgb[3] = { d2c(px[4 * i]), d2c(px[4 * i + 1]), d2c(px[4 * i + 2]) };
+                    fwrite(rgb, 1, 3, f);
+                }
             }
             fclose(f);
             printf("\tndt_b200: wrote %s\n", path);

@@ -867,6 +867,28 @@ static int aa_terminal(int aa_depth, double step)      /* ndt.c:663 */
     return aa_depth <= 0 || step < 1.0 / (2 << (aa_depth - 1));
 }
 
+/* colours of n samples; a list whose ray trees do not fit the record pool is split in two (like
+ * render_rows does with tiles), a tiny one gets a larger pool */
+static int aa_render_samples(ndt_b200_ctx *c, const double *d_xy, int n, double *d_samp, ndt_b200_stats *acc, int depth)
+{
+    c->sc.eye_override = 0;
+    int r = launch_pass(c, 0, 0, 0, 0, d_samp, NULL, NULL, NULL, NULL, true, true, d_xy, n);
+    if (!r) r = ndt_b200_sync(c);
+    if (r == NDT_B200_E_OVERFLOW && depth < 24) {
+        cudaStreamSynchronize(c->stream);
+        if (n >= 64) {
+            const int h1 = n / 2;
+            if ((r = aa_render_samples(c, d_xy, h1, d_samp, acc, depth + 1))) return r;
+            return aa_render_samples(c, d_xy + 2 * (size_t)h1, n - h1, d_samp + 4 * (size_t)h1, acc, depth + 1);
+        }
+        c->bounce_factor *= 4.0;
+        return aa_render_samples(c, d_xy, n, d_samp, acc, depth + 1);
+    }
+    if (r) return r;
+    stats_add(acc, &c->last);
+    return 0;
+}
+
 extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
                                   uint8_t *rgba_u8, double *rgba_f64, uint64_t *pixels_resampled,
                                   ndt_b200_stats *stats)
@@ -901,8 +923,14 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
     AA_CK(cudaMemsetAsync(d_res, 0, sizeof(unsigned long long), st));
 
     /* the initial image: one sample per corner (render_lines_thread with width+1, height+1) */
-    if ((r = ndt_b200_launch_tile(c, 0, 0, W + 1, H + 1, d_img, NULL, NULL, NULL, NULL))) goto aa_done;
-    if ((r = ndt_b200_sync(c))) goto aa_done;
+    for (int attempt = 0; ; ++attempt) {
+        r = ndt_b200_launch_tile(c, 0, 0, W + 1, H + 1, d_img, NULL, NULL, NULL, NULL);
+        if (!r) r = ndt_b200_sync(c);
+        if (r != NDT_B200_E_OVERFLOW || attempt >= 6) break;
+        cudaStreamSynchronize(st);
+        c->bounce_factor *= 2.0;        /* deep ray trees (glass, mirrors): a larger record pool */
+    }
+    if (r) goto aa_done;
     stats_add(&acc, &c->last);
 
     if (!(aa_depth >= 0 && aa_diff < 256)) {
@@ -926,10 +954,7 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
             /* this level's samples: one wavefront over the list */
             cudaFree(d_samp); d_samp = NULL;
             AA_CK(cudaMalloc(&d_samp, (size_t)n * 5 * 32));
-            c->sc.eye_override = 0;
-            if ((r = launch_pass(c, 0, 0, 0, 0, d_samp, NULL, NULL, NULL, NULL, true, true, d_xy, n * 5))) goto aa_done;
-            if ((r = ndt_b200_sync(c))) goto aa_done;
-            stats_add(&acc, &c->last);
+            if ((r = aa_render_samples(c, d_xy, n * 5, d_samp, &acc, 0))) goto aa_done;
             const int next_terminal = aa_terminal(aa_depth, step / 2);
             double *d_xy_next = NULL;
             if (!next_terminal) {
@@ -974,6 +999,49 @@ aa_done:
 }
 
 /* drop-in for render_image (ndt.c:900) */
+static ndt_b200_ctx *g_render_image_ctx = NULL;     /* one context per process, like the reference's global kdtree */
+
+/* render_image with the global recursive_aa set (ndt.c:44): the result is the 8-bit actual_img */
+extern "C" int ndt_b200_render_image_aa(void *scene, const void *kdtree, const ndt_b200_host_api *host,
+                                        char *name, char *depth_name, int width, int height,
+                                        int samples, int stereo_mode, int threads, int aa_diff,
+                                        int aa_depth, int max_optic_depth, int specular,
+                                        void *img_copy, void *depth_copy)
+{
+    (void)threads; (void)name; (void)depth_name; (void)depth_copy;
+    if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
+    if (stereo_mode != NDT_MONO) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "recursive anti-aliasing in stereo mode %d is not on the device path", stereo_mode);
+    int r;
+    if (!g_render_image_ctx && (r = ndt_b200_init(0, &g_render_image_ctx))) return r;
+    ndt_flat_scene *fs = NULL;
+    if ((r = ndt_b200_flatten_aa(scene, kdtree, width, height, max_optic_depth, specular, host, &fs))) return r;
+    {   /* render_image rescales the camera in place (ndt.c:925-926); callers rely on it */
+        ndtabi_scene *scn = (ndtabi_scene *)scene;
+        const double s = width / (double)height;
+        const int n = scn->cam.dirX.n, k = (n + 1) / 2;
+        for (int i = 0; i < 2 * k; ++i) scn->cam.dirX.v[i] = scn->cam.dirX.v[i] * s;
+    }
+    r = ndt_b200_upload(g_render_image_ctx, fs);
+    ndt_b200_free_flat(fs);
+    if (r) return r;
+    const size_t px = (size_t)width * height;
+    uint8_t *u8 = (uint8_t *)calloc(px, 4);
+    if (!u8) return ndt_set_error(NDT_B200_E_NOMEM, "out of memory");
+    r = ndt_b200_render_aa(g_render_image_ctx, aa_diff, aa_depth, u8, NULL, NULL, NULL);
+    if (r) { free(u8); return r; }
+    ndtabi_image *img = (ndtabi_image *)img_copy;
+    if (img) {      /* image_copy(img_copy, actual_img), ndt.c:1124-1127: 8-bit RGBA */
+        free(img->pixels);
+        memset(img, 0, sizeof *img);
+        img->width = width; img->height = height; img->pixel_width = 4;
+        img->allocated = (int)(px * 4);
+        img->pixels = u8;
+        u8 = NULL;
+    }
+    free(u8);
+    return 1;
+}
+
 extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_api *host,
                                      char *name, char *depth_name, int width, int height,
                                      int samples, int stereo_mode, int threads, int aa_diff,
@@ -982,7 +1050,7 @@ extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_
 {
     (void)threads; (void)aa_diff; (void)aa_depth; (void)name; (void)depth_name;
     if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
-    static ndt_b200_ctx *ctx = NULL;     /* one context per process, like the reference's global kdtree */
+    ndt_b200_ctx *&ctx = g_render_image_ctx;
     int r;
     if (!ctx && (r = ndt_b200_init(0, &ctx))) return r;
     ndt_flat_scene *fs = NULL;
