@@ -7,6 +7,7 @@
  */
 #pragma once
 #include <cuda_runtime.h>
+#include <float.h>
 #include "warp.cuh"
 
 using namespace ndt;
@@ -16,9 +17,6 @@ using namespace ndt;
 #endif
 #ifndef NDT_MIN_BLOCKS
 #define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
-#endif
-#ifndef NDT_SHADE_MIN_BLOCKS
-#define NDT_SHADE_MIN_BLOCKS 2
 #endif
 #ifndef NDT_TRACE_MIN_BLOCKS
 #define NDT_TRACE_MIN_BLOCKS 4   /* measured: 4 beats 2, 3 and 5 on config 2 */
@@ -42,11 +40,12 @@ struct GenArgs {
     uint32_t *mb_bits;
     uint32_t mb_stride, mb_words, mb_shift;
     const void *leafrec;     /* LeafRec<NP>[n_leaf_refs], leaf order (k_pack_leaf) */
+    const void *boxrec;      /* BoxRec<NP>[n_leaf_refs] */
 };
 
 /* leaf_refs[] -> LeafRec stream: one thread per reference, once per uploaded scene */
 template <int NP>
-__global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out)
+__global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out, BoxRec<NP> *box_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_refs) return;
@@ -65,7 +64,45 @@ __global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out)
             ((uint32_t)((nd + 1) / 2) << 16);
     r.geom_off = fo->geom_off;
     r.report_id = fo->report_id;
+    r.boxed = 0;
+    r.par_mask = 0x80000000u;
+    r.pad[0] = r.pad[1] = 0;
+    BoxRec<NP> bx;
+    for (int k = 0; k < NP; ++k) { bx.lo[k] = -FLT_MAX; bx.hi[k] = FLT_MAX; }
+    if (fo->type == NDT_T_ORTHOTOPE && bs[NP] > 0) {
+        /* the box of everything the orthotope can report as a hit (see box_hit in warp.cuh):
+         * p0 + sum s_a b_a, s_a in [-EPS, len_a + EPS], thickened by sqrt(2 EPS) = 0.0142; margins doubled */
+        const int m = fo->n_axes;
+        const double *g = sc.geom + fo->geom_off, *p0 = g, *basis = g + NP, *len = basis + (size_t)m * NP;
+        const double *bdb = len + m, *bdp = bdb + m;
+        for (int k = 0; k < sc.n; ++k) {
+            double lo = p0[k], hi = p0[k];
+            for (int a = 0; a < m; ++a) {
+                const double b = basis[(size_t)a * NP + k];
+                const double e0 = -2 * EPS * b, e1 = (len[a] + 2 * EPS) * b;
+                lo += e0 < e1 ? e0 : e1;
+                hi += e0 < e1 ? e1 : e0;
+            }
+            const double mg = 0.03 + 1e-9 * (fabs(lo) + fabs(hi));
+            /* stored as float, rounded outwards */
+            bx.lo[k] = __double2float_rd(lo - mg);
+            bx.hi[k] = __double2float_ru(hi + mg);
+        }
+        r.boxed = 1;
+        /* DIRECTIONAL lights whose shadow direction is (nearly) parallel to the flat: |P|^2 < EPS with
+         * the intersection's own arithmetic (orthotope.c:170-196) */
+        for (int l = 0; l < sc.n_lights && l < 31; ++l) {
+            if (sc.lights[l].type != NDT_L_DIRECTIONAL) continue;
+            double v[NP], o[NP], P[NP], Q[NP];
+            const double *lv = sc.geom + sc.lights[l].vec_off;
+            for (int k = 0; k < NP; ++k) { v[k] = lv[2 * NP + k]; o[k] = 0.0; }
+            axes_PQ<NP, LdGlobal>(o, v, p0, basis, bdb, bdp, m, P, Q);
+            const double qa = vdot<NP>(P, P);
+            if (!(qa >= EPS)) r.par_mask |= 1u << l;
+        }
+    }
     out[i] = r;
+    box_out[i] = bx;
 }
 
 template <int NP, bool CNT>
@@ -83,7 +120,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
     RayIn<NP> *rays = (RayIn<NP> *)a.rays;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage<NP> ws;
-    if (!CNT) ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(), a.leafrec, lane);
+    if (!CNT) ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
 
     while (true) {
         int base = 0;
@@ -231,7 +268,8 @@ struct WaveArgs {
     RayRec *rec;
     void *rays;              /* RayIn<NP>[cap - n0], slot s lives at rays[s - n0] */
     HitRec *hits;            /* [cap], by slot */
-    void *srays;             /* shadow queries RayIn<NP>[scap]: frac = dist_limit, depth = only-found flag */
+    void *srays;             /* shadow queries RayIn<NP>[scap]: frac = dist_limit, depth = 1 + light index for the
+                                any-hit query of a DIRECTIONAL light, else 0 */
     HitRec *shits;           /* [scap] */
     int *sslot;              /* [count * n_lights]: shadow slot of (ray, light) or -1 */
     int scap;
@@ -244,6 +282,7 @@ struct WaveArgs {
     uint32_t *mb_bits;
     uint32_t mb_stride, mb_words, mb_shift;
     const void *leafrec;
+    const void *boxrec;
     const double *samples_xy; /* generation 0 from an explicit list of pixel-space positions (ip, jp) instead of the
                                  tile's pixel grid: the sub-pixel samples of the recursive anti-aliasing */
 };
@@ -287,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
     mb.dirty = ~0ull;            /* first clear() wipes the whole column */
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage<NP> ws;
-    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(), a.leafrec, lane);
+    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
     int kd_overflow = 0;
     int count = a.count;
     if (MODE == 1) {             /* written by k_shade<A>, complete before this launch started */
@@ -303,7 +342,8 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         if (base >= count) break;
         const int r = base + lane;
         double o[NP], v[NP], limit = -1.0;
-        bool want, only_found = false;
+        bool want;
+        int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
         if (MODE == 0) {
             double frac; int depth, tx, ty;
             want = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
@@ -314,11 +354,11 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
                 NDT_UNROLL
                 for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
                 limit = in->frac;
-                only_found = in->depth != 0;
+                dir_light = in->depth - 1;
             }
         }
         Hit T;
-        trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, only_found);
+        trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
         if (ws.fault) break;     /* warp-uniform (warp.cuh) */
         if (want) {
             HitRec h;
@@ -333,7 +373,13 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
 
 /* PHASE 0 = A (emit the shadow queries), PHASE 1 = B (consume the answers, finish the ray) */
 template <int NP, int PHASE>
-__global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(const Scene sc, const WaveArgs a)
+#ifdef NDT_SHADE_MIN_BLOCKS
+__global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(
+#else
+/* no register cap: measured per dimension, a cap that helps NP=4 (3 CTA/SM) costs NP=10 more than it gains */
+__global__ void __launch_bounds__(BLOCK) k_shade(
+#endif
+const Scene sc, const WaveArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;     /* the grid covers count rounded up to whole warps */
@@ -377,7 +423,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(const Sce
                             NDT_UNROLL
                             for (int i = 0; i < NP; ++i) { out->o[i] = S.ro[i]; out->v[i] = S.rv[i]; }
                             out->frac = S.limit;
-                            out->depth = S.ltype == NDT_L_DIRECTIONAL ? 1 : 0;
+                            out->depth = S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0;   /* light index + 1: any-hit query */
                             out->pad = 0;
                         } else {
                             atomicExch(a.ctr + 2, 1);
@@ -475,7 +521,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS)
 k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in, const double *limits,
              int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
              uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
-             const void *leafrec)
+             const void *leafrec, const void *boxrec)
 {
     const int lane = threadIdx.x & 31;
     Mailbox mb;
@@ -485,7 +531,7 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
     mb.dirty = ~0ull;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage<NP> ws;
-    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(), leafrec, lane);
+    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), leafrec, sc.any_boxed ? boxrec : nullptr, lane);
     int ovf = 0;
     /* a warp takes 32 consecutive rays at a time; the loop bound is the same for all of its lanes */
     for (int r0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; r0 < n_rays; r0 += gridDim.x * blockDim.x) {
@@ -498,7 +544,7 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
             v[i] = (want && i < sc.n) ? v_in[(size_t)r * sc.n + i] : 0.0;
         }
         Hit T;
-        trace_kd_warp<NP>(sc, ws, mb, want, o, v, (want && limits) ? limits[r] : -1.0, T, ovf, false);
+        trace_kd_warp<NP>(sc, ws, mb, want, o, v, (want && limits) ? limits[r] : -1.0, T, ovf, -1);
         if (want) {
             double p[NP], nr[NP];
             vzero<NP>(p); vzero<NP>(nr);
@@ -516,15 +562,15 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
 
 /* launchers of one NP, filled in by np_inst.cu */
 struct NpOps {
-    int (*trace_blocks_per_sm)(void);
+    int (*trace_blocks_per_sm)(bool boxed);
     void (*trace)(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
     void (*shade)(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
-    int (*blocks_per_sm)(bool cnt);
+    int (*blocks_per_sm)(bool cnt, bool boxed);
     void (*generation)(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a);
-    void (*pack_leaf)(cudaStream_t st, const Scene &sc, int n_refs, void *out);
+    void (*pack_leaf)(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out);
     void (*trace_rays)(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const double *o, const double *v,
                        const double *limits, int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
                        uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
-                       const void *leafrec);
+                       const void *leafrec, const void *boxrec);
 };
 const NpOps *ndt_np_ops(int np);     /* NULL: dimension not built */

@@ -144,6 +144,7 @@ struct ndt_b200_ctx {
     /* scene */
     char *d_blob; size_t blob_cap;
     char *d_leafrec; size_t leafrec_cap;   /* LeafRec<npad>[n_leaf_refs] */
+    char *d_boxrec; size_t boxrec_cap;     /* BoxRec<npad>[n_leaf_refs] */
     ndt_flat_header hdr;
     Scene sc;
     int have_scene;
@@ -155,7 +156,7 @@ struct ndt_b200_ctx {
     char *d_srays; size_t srays_bytes;   /* shadow queries of one generation */
     HitRec *d_shits; size_t shits_cap;
     int *d_sslot; size_t sslot_cap;
-    int trace_grid[8];                   /* cached k_trace occupancy per NP/2 */
+    int trace_grid[2][8];                /* cached k_trace occupancy per (boxed scene, NP/2) */
     char *d_ana; size_t ana_bytes;       /* ANAGLYPH_3D: the two eyes' fp64 frames */
     int *d_ctr;                          /* [0] tail [1] next [2..3] overflow [4] shadow tail [5] shadow next */
     unsigned long long *d_stats;         /* 8 counters */
@@ -165,16 +166,16 @@ struct ndt_b200_ctx {
     double bounce_factor;
     uint32_t options;
     ndt_b200_stats last;
-    int grid_blocks[2][8];               /* cached occupancy per (CNT, NP/2) */
+    int grid_blocks[4][8];               /* cached occupancy per (CNT + 2 * boxed scene, NP/2) */
     int light_type[256];                 /* host copy of lights[].type (which lights can ask a shadow query) */
 };
 
 static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
 {
-    int &g = c->grid_blocks[cnt ? 1 : 0][np / 2];
+    int &g = c->grid_blocks[(cnt ? 1 : 0) + (c->sc.any_boxed ? 2 : 0)][np / 2];
     if (g == 0) {
         const NpOps *ops = ndt_np_ops(np);
-        g = (ops ? ops->blocks_per_sm(cnt) : 1) * c->sm_count;
+        g = (ops ? ops->blocks_per_sm(cnt, c->sc.any_boxed != 0) : 1) * c->sm_count;
     }
     return g;
 }
@@ -191,8 +192,8 @@ static int grow(ndt_b200_ctx *c, void **p, size_t *cap, size_t want_bytes)
 
 static int trace_grid_for(ndt_b200_ctx *c, int np)
 {
-    int &g = c->trace_grid[np / 2];
-    if (g == 0) g = ndt_np_ops(np)->trace_blocks_per_sm() * c->sm_count;
+    int &g = c->trace_grid[c->sc.any_boxed ? 1 : 0][np / 2];
+    if (g == 0) g = ndt_np_ops(np)->trace_blocks_per_sm(c->sc.any_boxed != 0) * c->sm_count;
     return g;
 }
 
@@ -232,7 +233,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
+    cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
     cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_sslot);
     cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out);
     cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats);
@@ -290,6 +291,12 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     s.view = h->off_view ? (const double *)(b + h->off_view) : NULL;
     s.cam_type = h->cam_type; s.stereo_mode = h->stereo_mode; s.view_eyes = h->view_eyes;
     s.eye_override = 0; s.cam_dist = h->cam_dist;
+    s.any_boxed = 0;
+    {   /* k_pack_leaf gives orthotopes with a bounding sphere a box (warp.cuh: box_hit) */
+        const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
+        for (int i = 0; i < h->n_items && !s.any_boxed; ++i)
+            if (ho[i].type == NDT_T_ORTHOTOPE && ho[i].bs_radius > 0) s.any_boxed = 1;
+    }
     if (h->n_lights > 256) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d lights (limit 256)", h->n_lights);
     {
         const ndt_flat_light *hl = (const ndt_flat_light *)((const char *)fs + h->off_lights);
@@ -299,7 +306,7 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
         return ndt_set_error(NDT_B200_E_UNSUPPORTED, "kd-tree depth %d exceeds the traversal stack (%d)", h->tree_depth, KD_STACK);
     /* the leaf-ordered record stream the warps stage through shared memory (warp.cuh) */
     {
-        const size_t recb = (size_t)(h->npad + 2) * 8 + 16;
+        const size_t recb = (size_t)h->npad * 8 + 48;       /* sizeof(LeafRec<npad>), warp.cuh */
         const size_t need = (size_t)(h->n_leaf_refs > 0 ? h->n_leaf_refs : 1) * recb;
         if (c->leafrec_cap < need) {
             CK(cudaStreamSynchronize(c->stream));
@@ -308,7 +315,8 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
             c->leafrec_cap = need + need / 4;
         }
         if (h->n_leaf_refs > 0) {
-            ndt_np_ops(h->npad)->pack_leaf(c->stream, s, h->n_leaf_refs, c->d_leafrec);
+            if ((r = grow(c, (void **)&c->d_boxrec, &c->boxrec_cap, (size_t)h->n_leaf_refs * (size_t)h->npad * 8))) return r;
+            ndt_np_ops(h->npad)->pack_leaf(c->stream, s, h->n_leaf_refs, c->d_leafrec, c->d_boxrec);
             CK(cudaGetLastError());
         }
     }
@@ -454,6 +462,7 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
         a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
         a.mb_words = mb_words; a.mb_shift = mb_shift;
         a.leafrec = c->d_leafrec;
+        a.boxrec = c->d_boxrec;
         a.samples_xy = d_samples;
         while (count > 0) {
             if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
@@ -507,6 +516,7 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
     a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
     a.mb_words = mb_words; a.mb_shift = mb_shift;
     a.leafrec = c->d_leafrec;
+    a.boxrec = c->d_boxrec;
     while (count > 0) {
         if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
         gstart[ngen] = start; gcount[ngen] = count;
@@ -673,7 +683,7 @@ extern "C" int ndt_b200_trace_rays(ndt_b200_ctx *c, int n_rays, const double *or
     if (e == cudaSuccess) {
         ndt_np_ops(np)->trace_rays(blocks, st, c->sc, n_rays, d_o, d_v, dist_limits ? d_lim : NULL, d_found, d_id, d_t,
                                    d_hit, d_nrm, c->d_mb, (uint32_t)(blocks * BLOCK), words, shift, c->d_ctr + 2,
-                                   c->d_leafrec);
+                                   c->d_leafrec, c->d_boxrec);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(found, d_found, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, st);

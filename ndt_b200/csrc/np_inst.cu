@@ -12,29 +12,29 @@
 namespace {
 constexpr int NP = NDT_NP;
 
-template <bool CNT> size_t generation_smem() { return CNT ? 0 : (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(); }
+template <bool CNT> size_t generation_smem(bool boxed) { return CNT ? 0 : (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(boxed); }
 
-template <bool CNT> int occ()
+template <bool CNT> int occ(bool boxed)
 {
     int b = 0;
-    const size_t sm = generation_smem<CNT>();
+    const size_t sm = generation_smem<CNT>(boxed);
     if (sm > 48 * 1024) cudaFuncSetAttribute(k_generation<NP, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generation<NP, CNT>, BLOCK, sm) != cudaSuccess || b < 1) b = 1;
     return b;
 }
-int blocks_per_sm(bool cnt) { return cnt ? occ<true>() : occ<false>(); }
+int blocks_per_sm(bool cnt, bool boxed) { return cnt ? occ<true>(boxed) : occ<false>(boxed); }
 
 void generation(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
 {
-    if (cnt) k_generation<NP, true><<<blocks, BLOCK, generation_smem<true>(), st>>>(sc, a);
-    else k_generation<NP, false><<<blocks, BLOCK, generation_smem<false>(), st>>>(sc, a);
+    if (cnt) k_generation<NP, true><<<blocks, BLOCK, generation_smem<true>(sc.any_boxed != 0), st>>>(sc, a);
+    else k_generation<NP, false><<<blocks, BLOCK, generation_smem<false>(sc.any_boxed != 0), st>>>(sc, a);
 }
 
-size_t trace_smem() { return (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(); }
-int trace_blocks_per_sm()
+size_t trace_smem(bool boxed) { return (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(boxed); }
+int trace_blocks_per_sm(bool boxed)
 {
     int b0 = 0, b1 = 0;
-    const size_t sm = trace_smem();
+    const size_t sm = trace_smem(boxed);
     if (sm > 48 * 1024) {
         cudaFuncSetAttribute(k_trace<NP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         cudaFuncSetAttribute(k_trace<NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -45,8 +45,8 @@ int trace_blocks_per_sm()
 }
 void trace(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
 {
-    if (mode) k_trace<NP, 1><<<blocks, BLOCK, trace_smem(), st>>>(sc, a);
-    else k_trace<NP, 0><<<blocks, BLOCK, trace_smem(), st>>>(sc, a);
+    if (mode) k_trace<NP, 1><<<blocks, BLOCK, trace_smem(sc.any_boxed != 0), st>>>(sc, a);
+    else k_trace<NP, 0><<<blocks, BLOCK, trace_smem(sc.any_boxed != 0), st>>>(sc, a);
 }
 void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
 {
@@ -54,18 +54,20 @@ void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveAr
     else k_shade<NP, 0><<<blocks, BLOCK, 0, st>>>(sc, a);
 }
 
-void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out)
+void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out)
 {
-    k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out);
+    k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out, (BoxRec<NP> *)box_out);
 }
 
 void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const double *o, const double *v,
                 const double *limits, int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
                 uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
-                const void *leafrec)
+                const void *leafrec, const void *boxrec)
 {
-    k_trace_rays<NP><<<blocks, BLOCK, (BLOCK / 32) * warp_smem_bytes<NP>(), st>>>(
-        sc, n_rays, o, v, limits, found, ids, ts, hits, normals, mb_bits, mb_stride, mb_words, mb_shift, overflow, leafrec);
+    const size_t sm = (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(sc.any_boxed != 0);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k_trace_rays<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k_trace_rays<NP><<<blocks, BLOCK, sm, st>>>(
+        sc, n_rays, o, v, limits, found, ids, ts, hits, normals, mb_bits, mb_stride, mb_words, mb_shift, overflow, leafrec, boxrec);
 }
 }  // namespace
 

@@ -56,7 +56,18 @@ template <int NP> struct LeafRec {
     uint32_t tfa;         /* type | flags << 4 | n_axes << 8 | (16-byte units of the geometry block, 0 = not staged) << 16 */
     uint32_t geom_off;
     int32_t report_id;
-};                        /* (NP + 2) * 8 + 16 bytes, a multiple of 16 */
+    /* the box cull (see box_hit): */
+    uint32_t boxed;       /* 1: lo/hi bound every point the primitive can report as a hit */
+    uint32_t par_mask;    /* bit L: DIRECTIONAL light L runs (nearly) parallel to the primitive's flat, its shadow
+                             queries must not be culled */
+    uint32_t pad[2];
+};                        /* 8 NP + 48 bytes, a multiple of 16 */
+
+/* the boxes of the box cull, a second stream parallel to LeafRec[] that is only staged for scenes that
+ * have boxed primitives (Scene::any_boxed) */
+template <int NP> struct BoxRec {
+    float lo[NP], hi[NP];
+};                        /* 8 NP bytes, a multiple of 16 */
 
 /* doubles of the largest geometry block staged in shared memory (ndt_flat.h layouts):
  * an orthotope / hcylinder with NP axes, or a facet */
@@ -80,10 +91,12 @@ __host__ __device__ inline int geom_block_doubles(int type, int m, int np)
     return 0;
 }
 
-/* per warp: two LeafRec chunks, two geometry blocks, four mbarriers */
-template <int NP> __host__ __device__ constexpr int warp_smem_bytes()
+/* per warp: two LeafRec chunks, two geometry blocks, four mbarriers and -- only for scenes with boxed
+ * primitives -- two BoxRec chunks (dynamic shared memory: the launch asks for what the scene needs) */
+template <int NP> __host__ __device__ constexpr int warp_smem_bytes(bool boxed)
 {
-    return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 2 * geom_max_doubles<NP>() * 8 + 32;
+    return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 2 * geom_max_doubles<NP>() * 8 + 32 +
+           (boxed ? 2 * CHUNK * (int)sizeof(BoxRec<NP>) : 0);
 }
 
 /* ---- mbarrier + TMA bulk copy (PTX ISA: cp.async.bulk, mbarrier) ------------- */
@@ -119,20 +132,25 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
 /* per-warp staging area and its pipeline state */
 template <int NP> struct WarpStage {
     LeafRec<NP> *buf[2];
+    BoxRec<NP> *bbuf[2];  /* the chunk's boxes (only filled when boxes != NULL) */
     double *gbuf[2];      /* staged geometry blocks */
     uint64_t *bar;        /* bar[0..1]: record chunks, bar[2..3]: geometry blocks */
     uint32_t phase;       /* bit s = parity the next wait on bar[s] uses */
     const LeafRec<NP> *stream;
+    const BoxRec<NP> *boxes;   /* NULL: the scene has no boxed primitive */
     int lane;
     int fault;            /* a bounded wait ran out */
 
-    __device__ __forceinline__ void init(unsigned char *smem, const void *leafrec, int lane_)
+    __device__ __forceinline__ void init(unsigned char *smem, const void *leafrec, const void *boxrec, int lane_)
     {
         buf[0] = reinterpret_cast<LeafRec<NP> *>(smem);
         buf[1] = buf[0] + CHUNK;
-        gbuf[0] = reinterpret_cast<double *>(smem + 2 * CHUNK * sizeof(LeafRec<NP>));
+        boxes = static_cast<const BoxRec<NP> *>(boxrec);
+        gbuf[0] = reinterpret_cast<double *>(buf[1] + CHUNK);
         gbuf[1] = gbuf[0] + geom_max_doubles<NP>();
         bar = reinterpret_cast<uint64_t *>(gbuf[1] + geom_max_doubles<NP>());
+        bbuf[0] = reinterpret_cast<BoxRec<NP> *>(bar + 4);      /* present only when boxes != NULL */
+        bbuf[1] = bbuf[0] + CHUNK;
         phase = 0;
         stream = static_cast<const LeafRec<NP> *>(leafrec);
         lane = lane_;
@@ -152,8 +170,10 @@ template <int NP> struct WarpStage {
     {
         if (lane == 0 && !fault) {
             const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(LeafRec<NP>);
-            mbar_expect_tx(bar + s, bytes);
+            const uint32_t bbytes = boxes ? (uint32_t)cnt * (uint32_t)sizeof(BoxRec<NP>) : 0u;
+            mbar_expect_tx(bar + s, bytes + bbytes);
             bulk_g2s(buf[s], stream + first, bytes, bar + s);
+            if (boxes) bulk_g2s(bbuf[s], boxes + first, bbytes, bar + s);
         }
     }
     /* lane 0 starts the copy of a geometry block (n16 16-byte units at geom[off]) into gbuf[g] */
@@ -174,6 +194,49 @@ template <int NP> struct WarpStage {
         phase ^= 1u << s;
     }
 };
+
+/* ---- the box cull -------------------------------------------------------------------------
+ * Not in the reference: a test that can only REMOVE intersection tests whose answer is "no hit".
+ * The bounding spheres of ndt are loose for flat primitives (a 5-face of the 8-cube has the
+ * sphere of the whole cube): in BASELINE config 2, 43 % of the objects of a leaf pass the sphere
+ * test, 99 % of those then miss (tools/workload_stats.py).  An orthotope can only report a hit
+ * point p0 + sum s_a b_a + d with s_a in [-EPS, len_a + EPS] (orthotope.c:122-148) and |d|^2 <=
+ * 2 EPS (the quadratic's "qc -= EPSILON", orthotope.c:199, and its closest-approach fallback
+ * |dist| <= EPSILON, :262): k_pack_leaf bounds that set by an axis-aligned box with a margin, and
+ * a ray that misses the box cannot hit.  trace() has no state that a missing "no hit" would
+ * change (object.c:715-733: only a hit touches min_dist or breaks), and a culled object needs no
+ * mailbox bit for the same reason as an object failing the sphere test (header of this file).
+ *
+ * The one way a "no hit" differs from the reference's answer is its NaN / infinity path: for a
+ * ray (nearly) parallel to the flat, |P|^2 < EPS, orthotope.c:236-242 divides by a qb that can be
+ * exactly zero and then reports a hit at t = +-inf.  For every kind of query but one that answer
+ * is inert (NaN / inf distances are never accepted over a finite one, never "< dist_limit", and
+ * an accepted inf never reaches the kd result: trace_kd_warp's `lmd < lt`).  The exception is the
+ * any-hit query of a DIRECTIONAL light (dist_limit == 0.0 breaks on ANY reported hit,
+ * object.c:729).  All queries of one such light share one direction, so k_pack_leaf evaluates
+ * |P|^2 for (primitive, light) with the intersection's own arithmetic (axes_PQ) and flags the
+ * pairs below EPS: those are never culled.
+ * ------------------------------------------------------------------------------------------- */
+template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const float *hi, const double *o, const double *vinv)
+{
+    double tmin = 0.0, tmax = DBL_MAX;
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 4) {
+        const float4 l4 = *reinterpret_cast<const float4 *>(lo + i);
+        const float4 h4 = *reinterpret_cast<const float4 *>(hi + i);
+        const float l[4] = { l4.x, l4.y, l4.z, l4.w }, h[4] = { h4.x, h4.y, h4.z, h4.w };
+        NDT_UNROLL
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < NP) {
+                const double t1 = ((double)l[k] - o[i + k]) * vinv[i + k];
+                const double t2 = ((double)h[k] - o[i + k]) * vinv[i + k];
+                tmin = fmax(tmin, fmin(t1, t2));        /* fmin / fmax drop a NaN operand (0 * inf): no constraint */
+                tmax = fmin(tmax, fmax(t1, t2));
+            }
+        }
+    }
+    return tmin <= tmax;
+}
 
 /* the ray-only half of bounding.c:34-85: desc = (v.oc)^2 - |oc|^2 + r^2 */
 template <int NP> __device__ __forceinline__ bool bsphere_ray_part(const double *c, double r2, const double *o, const double *v)
@@ -242,8 +305,8 @@ __device__ __forceinline__ double trace_list_slow(const Scene &sc, const int32_t
  * (<0: nothing accepted), out_id, out_win. */
 template <int NP>
 __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, int first, int count, bool mine,
-                                            Mailbox &mb, const double *o, const double *v, double dist_limit,
-                                            int &out_id, int &out_win)
+                                            Mailbox &mb, const double *o, const double *v, const double *vinv_box,
+                                            uint32_t keep_mask, double dist_limit, int &out_id, int &out_win)
 {
     double min_dist = -1;
     out_id = -1;
@@ -277,7 +340,13 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                 double c[NP];
                 lds_vec<NP>(c, rp);
                 const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);   /* r2, r */
-                const bool pass = !(rr.y > 0) || bsphere_ray_part<NP>(c, rr.x, o, v);
+                bool pass = !(rr.y > 0) || bsphere_ray_part<NP>(c, rr.x, o, v);
+#ifndef NDT_NO_BOX_CULL
+                if (pass && ws.boxes) {
+                    const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);    /* boxed, par_mask */
+                    if (bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(ws.bbuf[s][k].lo, ws.bbuf[s][k].hi, o, vinv_box);
+                }
+#endif
                 cand |= (pass ? 1u : 0u) << k;
             }
         }
@@ -375,12 +444,18 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
 template <int NP>
 __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool want,
                                               const double *o, const double *v, double dist_limit,
-                                              Hit &out, int &overflow, bool only_found)
+                                              Hit &out, int &overflow, int dir_light)
 {
+    /* dir_light >= 0: the any-hit query of DIRECTIONAL light dir_light (ndt.c:241-249): the caller consumes
+     * nothing but the return value */
+    const bool only_found = dir_light >= 0;
+    /* primitives this query must not box-cull (see box_hit): bit 31 of par_mask is always set */
+    const uint32_t keep_mask = dir_light < 0 ? 0u : (dir_light < 31 ? 1u << dir_light : 0x80000000u);
+
     /* per-axis values the walk indexes by the split dimension live in local memory; the loops
      * that fill them stay rolled (one copy of the fp64 division sequence instead of NP or 2 NP:
      * this per-ray prologue runs once per query and only costs instruction fetches) */
-    double o_dyn[NP], v_dyn[NP], vinv[NP];
+    double o_dyn[NP], v_dyn[NP], vinv[NP], vbox[NP];
     double t = DBL_MAX, md = -1;
     int ret = 0;
     out.id = -1;
@@ -397,7 +472,11 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
             else r = 1.0 / vi;
             vinv[i] = r;
+#ifndef NDT_NO_BOX_CULL
+            if (sc.any_boxed) vbox[i] = 1.0 / vi;   /* the slab test wants the true reciprocal (+-inf for a zero component) */
+#endif
         }
+
         /* infinite objects first, linear, no mailbox (kd-tree.c:592-594) */
         md = trace_list_slow_impl<NP>(sc, sc.inf, sc.n_inf, 0, o_dyn, v_dyn, dist_limit, &out.id, &out.win);
         ret = !(md < 0);
@@ -503,7 +582,9 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             const bool mine = leaf_node == L;
             waiting &= ~__ballot_sync(FULL, mine);
             int oid, owin;
-            const double lmd = warp_leaf<NP>(sc, ws, first, count, mine, mb, o, v, dist_limit, oid, owin);
+            /* vbox stays in local memory: it is only read by the box test of boxed scenes, and sixteen
+             * more registers across the whole walk cost every scene */
+            const double lmd = warp_leaf<NP>(sc, ws, first, count, mine, mb, o, v, vbox, keep_mask, dist_limit, oid, owin);
             if (mine && !(lmd < 0)) {
                 lret = 1;
                 if (lmd < lt) {          /* trace sets t only when min_dist > EPS, which holds here */
@@ -550,7 +631,7 @@ __device__ __forceinline__ void process_ray_warp(const Scene &sc, WarpStage<NP> 
             continue;
         }
         Hit T;
-        trace_kd_warp<NP>(sc, ws, mb, want, S.ro, S.rv, S.limit, T, overflow, S.ltype == NDT_L_DIRECTIONAL);
+        trace_kd_warp<NP>(sc, ws, mb, want, S.ro, S.rv, S.limit, T, overflow, S.ltype == NDT_L_DIRECTIONAL ? it : -1);
         if (want) shade_after<NP, false>(sc, S, it, T, src, look, rec, prim_hit, prim_id, prim_dist, none);
         if (it < 0 && !__ballot_sync(FULL, active && S.shaded)) break;
     }

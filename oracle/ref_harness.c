@@ -188,6 +188,24 @@ int refh_begin_frame(int dims, int frame, int frames, const char *cfg, double *k
 
     scene_validate_objects(&g_scn);
     camera_aim(&g_scn.cam);
+    /* The plugins prepare themselves lazily on their first intersect() behind a double-checked lock whose
+     * flag is a bit-field next to `transparent` (object.h:24, e.g. orthotope.c:23-54,152): with many render
+     * threads the first rays race on it and the reference occasionally dereferences a NULL `prepped`
+     * (seen as a SIGSEGV of the test process on the 16-core GPU box).  One ray per object from this thread
+     * runs every prepare() up front; the prepared values do not depend on the ray. */
+    {
+        vectNd o, v, r, nrm;
+        vectNd_calloc(&o, g_scn.dimensions);
+        vectNd_calloc(&v, g_scn.dimensions);
+        vectNd_calloc(&r, g_scn.dimensions);
+        vectNd_calloc(&nrm, g_scn.dimensions);
+        vectNd_set(&v, 0, 1.0);
+        for (int i = 0; i < g_nflat; ++i) {
+            object *hit = NULL;
+            g_flat[i]->intersect(g_flat[i], &o, &v, &r, &nrm, &hit);
+        }
+        vectNd_free(&o); vectNd_free(&v); vectNd_free(&r); vectNd_free(&nrm);
+    }
     hush(0);
     g_frame_open = 1;
     g_dirx_scaled = 0;

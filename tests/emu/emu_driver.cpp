@@ -38,7 +38,7 @@ static int run(const void *blob, int x0, int y0, int tw, int th, double *f64, ui
     s.focal_scale = h->focal_scale;
     s.view = h->off_view ? (const double *)(b + h->off_view) : nullptr;
     s.cam_type = h->cam_type; s.stereo_mode = h->stereo_mode; s.view_eyes = h->view_eyes;
-    s.eye_override = eye_override; s.cam_dist = h->cam_dist;
+    s.eye_override = eye_override; s.cam_dist = h->cam_dist; s.any_boxed = 0;
 
     const int bpr = (tw + 7) / 8, brows = (th + 3) / 4, n0 = bpr * brows * 32;
     std::vector<RayRec> rec(n0);

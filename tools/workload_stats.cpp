@@ -5,6 +5,7 @@
 #define NDT_STATS 1
 #include "../tests/emu/emu_driver.cpp"
 NdtStats ndt_stats;
+bool ndt_stats_box_miss = false;
 extern "C" void emu_stats_reset() { memset(&ndt_stats, 0, sizeof ndt_stats); }
 extern "C" void emu_stats_get(unsigned long long *out) { memcpy(out, &ndt_stats, sizeof ndt_stats); }
 extern "C" int emu_stats_words() { return (int)(sizeof ndt_stats / sizeof(unsigned long long)); }
