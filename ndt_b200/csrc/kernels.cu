@@ -296,6 +296,20 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
         const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
         for (int i = 0; i < h->n_items && !s.any_boxed; ++i)
             if (ho[i].type == NDT_T_ORTHOTOPE && ho[i].bs_radius > 0) s.any_boxed = 1;
+        /* the slab test runs in fp32 with a fixed margin (warp.cuh: box_hit): only for scenes whose
+         * coordinates keep its rounding error far below that margin */
+        if (s.any_boxed) {
+            const double *bb = (const double *)((const char *)fs + h->off_aabb);
+            const double *cm = (const double *)((const char *)fs + h->off_camera);
+            const double *gg = (const double *)((const char *)fs + h->off_geom);
+            const ndt_flat_light *hl2 = (const ndt_flat_light *)((const char *)fs + h->off_lights);
+            double ext = 0.0;
+            for (int i = 0; i < 2 * h->npad; ++i) if (fabs(bb[i]) > ext) ext = fabs(bb[i]);
+            for (int i = 0; i < h->npad; ++i) if (fabs(cm[i]) > ext) ext = fabs(cm[i]);
+            for (int l = 0; l < h->n_lights; ++l)
+                for (int i = 0; i < h->npad; ++i) if (fabs(gg[hl2[l].vec_off + i]) > ext) ext = fabs(gg[hl2[l].vec_off + i]);
+            if (!(ext < 2e4)) s.any_boxed = 0;
+        }
     }
     if (h->n_lights > 256) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d lights (limit 256)", h->n_lights);
     {

@@ -217,9 +217,14 @@ template <int NP> struct WarpStage {
  * |P|^2 for (primitive, light) with the intersection's own arithmetic (axes_PQ) and flags the
  * pairs below EPS: those are never culled.
  * ------------------------------------------------------------------------------------------- */
-template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const float *hi, const double *o, const double *vinv)
+/* The slab test runs in fp32 (full-rate pipe, native min/max that drop a NaN operand) and BEFORE the
+ * fp64 sphere test, which then only sees the ~1 % of boxed objects that pass.  Rounding: every fp32 step
+ * moves a box face by at most ~2^-22 * max(|coordinate|, |origin|) in position space; the box carries
+ * 0.03 of margin where 0.0142 is needed, and ndt_b200_upload switches the cull off for scenes whose
+ * coordinates exceed 2e4 (error 5e-3). */
+template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const float *hi, const float *of, const float *vif)
 {
-    double tmin = 0.0, tmax = DBL_MAX;
+    float tmin = 0.0f, tmax = FLT_MAX;
     NDT_UNROLL
     for (int i = 0; i < NP; i += 4) {
         const float4 l4 = *reinterpret_cast<const float4 *>(lo + i);
@@ -228,14 +233,15 @@ template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const
         NDT_UNROLL
         for (int k = 0; k < 4; ++k) {
             if (i + k < NP) {
-                const double t1 = ((double)l[k] - o[i + k]) * vinv[i + k];
-                const double t2 = ((double)h[k] - o[i + k]) * vinv[i + k];
-                tmin = fmax(tmin, fmin(t1, t2));        /* fmin / fmax drop a NaN operand (0 * inf): no constraint */
-                tmax = fmin(tmax, fmax(t1, t2));
+                const float t1 = __fmul_rn(__fsub_rn(l[k], of[i + k]), vif[i + k]);
+                const float t2 = __fmul_rn(__fsub_rn(h[k], of[i + k]), vif[i + k]);
+                tmin = fmaxf(tmin, fminf(t1, t2));      /* fminf / fmaxf drop a NaN operand (0 * inf): no constraint */
+                tmax = fminf(tmax, fmaxf(t1, t2));
             }
         }
     }
-    return tmin <= tmax;
+    /* one more ulp-scale allowance on the comparison itself */
+    return tmin <= tmax * 1.000001f + 1e-30f;
 }
 
 /* the ray-only half of bounding.c:34-85: desc = (v.oc)^2 - |oc|^2 + r^2 */
@@ -305,8 +311,9 @@ __device__ __forceinline__ double trace_list_slow(const Scene &sc, const int32_t
  * (<0: nothing accepted), out_id, out_win. */
 template <int NP>
 __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, int first, int count, bool mine,
-                                            Mailbox &mb, const double *o, const double *v, const double *vinv_box,
-                                            uint32_t keep_mask, double dist_limit, int &out_id, int &out_win)
+                                            Mailbox &mb, const double *o, const double *v, const float *obox,
+                                            const float *vbox, uint32_t keep_mask, double dist_limit,
+                                            int &out_id, int &out_win)
 {
     double min_dist = -1;
     out_id = -1;
@@ -334,20 +341,35 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
         /* broad phase */
         unsigned cand = 0;
         if (live) {
-            NDT_BROAD_LOOP
-            for (int k = 0; k < cnt; ++k) {
-                const double *rp = reinterpret_cast<const double *>(rec + k);
-                double c[NP];
-                lds_vec<NP>(c, rp);
-                const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);   /* r2, r */
-                bool pass = !(rr.y > 0) || bsphere_ray_part<NP>(c, rr.x, o, v);
-#ifndef NDT_NO_BOX_CULL
-                if (pass && ws.boxes) {
+            if (ws.boxes) {
+                /* boxed scene: the fp32 slab test first, the sphere test for what is left */
+                float of[NP], vif[NP];
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) { of[i] = obox[i]; vif[i] = vbox[i]; }
+                NDT_BROAD_LOOP
+                for (int k = 0; k < cnt; ++k) {
+                    const double *rp = reinterpret_cast<const double *>(rec + k);
                     const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);    /* boxed, par_mask */
-                    if (bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(ws.bbuf[s][k].lo, ws.bbuf[s][k].hi, o, vinv_box);
+                    bool pass = true;
+                    if (bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(ws.bbuf[s][k].lo, ws.bbuf[s][k].hi, of, vif);
+                    if (pass) {
+                        double c[NP];
+                        lds_vec<NP>(c, rp);
+                        const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);   /* r2, r */
+                        pass = !(rr.y > 0) || bsphere_ray_part<NP>(c, rr.x, o, v);
+                    }
+                    cand |= (pass ? 1u : 0u) << k;
                 }
-#endif
-                cand |= (pass ? 1u : 0u) << k;
+            } else {
+                NDT_BROAD_LOOP
+                for (int k = 0; k < cnt; ++k) {
+                    const double *rp = reinterpret_cast<const double *>(rec + k);
+                    double c[NP];
+                    lds_vec<NP>(c, rp);
+                    const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);   /* r2, r */
+                    const bool pass = !(rr.y > 0) || bsphere_ray_part<NP>(c, rr.x, o, v);
+                    cand |= (pass ? 1u : 0u) << k;
+                }
             }
         }
 
@@ -455,7 +477,8 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
     /* per-axis values the walk indexes by the split dimension live in local memory; the loops
      * that fill them stay rolled (one copy of the fp64 division sequence instead of NP or 2 NP:
      * this per-ray prologue runs once per query and only costs instruction fetches) */
-    double o_dyn[NP], v_dyn[NP], vinv[NP], vbox[NP];
+    double o_dyn[NP], v_dyn[NP], vinv[NP];
+    float obox[NP], vbox[NP];       /* the ray in fp32 for the box cull (local memory; registers only inside the broad loop) */
     double t = DBL_MAX, md = -1;
     int ret = 0;
     out.id = -1;
@@ -472,9 +495,10 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
             else r = 1.0 / vi;
             vinv[i] = r;
-#ifndef NDT_NO_BOX_CULL
-            if (sc.any_boxed) vbox[i] = 1.0 / vi;   /* the slab test wants the true reciprocal (+-inf for a zero component) */
-#endif
+            if (sc.any_boxed) {         /* the slab test wants the true reciprocal (+-inf for a zero component) */
+                obox[i] = (float)o_dyn[i];
+                vbox[i] = (float)(1.0 / vi);
+            }
         }
 
         /* infinite objects first, linear, no mailbox (kd-tree.c:592-594) */
@@ -582,9 +606,7 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             const bool mine = leaf_node == L;
             waiting &= ~__ballot_sync(FULL, mine);
             int oid, owin;
-            /* vbox stays in local memory: it is only read by the box test of boxed scenes, and sixteen
-             * more registers across the whole walk cost every scene */
-            const double lmd = warp_leaf<NP>(sc, ws, first, count, mine, mb, o, v, vbox, keep_mask, dist_limit, oid, owin);
+            const double lmd = warp_leaf<NP>(sc, ws, first, count, mine, mb, o, v, obox, vbox, keep_mask, dist_limit, oid, owin);
             if (mine && !(lmd < 0)) {
                 lret = 1;
                 if (lmd < lt) {          /* trace sets t only when min_dist > EPS, which holds here */
