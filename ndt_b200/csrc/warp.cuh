@@ -131,10 +131,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity)
 
 /* per-warp staging area and its pipeline state */
 template <int NP> struct WarpStage {
-    LeafRec<NP> *buf[2];
-    BoxRec<NP> *bbuf[2];  /* the chunk's boxes (only filled when boxes != NULL) */
-    double *gbuf[2];      /* staged geometry blocks */
+    /* one base pointer each and arithmetic on the buffer index: an array of pointers indexed by a
+     * run-time value lives in local memory, and every buf[s] in the leaf loop was a local load
+     * (ncu: long_scoreboard on exactly those lines) */
+    LeafRec<NP> *buf0;    /* two chunks of CHUNK records */
+    BoxRec<NP> *bbuf0;    /* the chunks' boxes (only present / filled when boxes != NULL) */
+    double *gbuf0;        /* two staged geometry blocks of geom_max_doubles<NP>() */
     uint64_t *bar;        /* bar[0..1]: record chunks, bar[2..3]: geometry blocks */
+    __device__ __forceinline__ LeafRec<NP> *buf(int s) const { return buf0 + s * CHUNK; }
+    __device__ __forceinline__ BoxRec<NP> *bbuf(int s) const { return bbuf0 + s * CHUNK; }
+    __device__ __forceinline__ double *gbuf(int g) const { return gbuf0 + g * geom_max_doubles<NP>(); }
     uint32_t phase;       /* bit s = parity the next wait on bar[s] uses */
     const LeafRec<NP> *stream;
     const BoxRec<NP> *boxes;   /* NULL: the scene has no boxed primitive */
@@ -143,14 +149,11 @@ template <int NP> struct WarpStage {
 
     __device__ __forceinline__ void init(unsigned char *smem, const void *leafrec, const void *boxrec, int lane_)
     {
-        buf[0] = reinterpret_cast<LeafRec<NP> *>(smem);
-        buf[1] = buf[0] + CHUNK;
+        buf0 = reinterpret_cast<LeafRec<NP> *>(smem);
         boxes = static_cast<const BoxRec<NP> *>(boxrec);
-        gbuf[0] = reinterpret_cast<double *>(buf[1] + CHUNK);
-        gbuf[1] = gbuf[0] + geom_max_doubles<NP>();
-        bar = reinterpret_cast<uint64_t *>(gbuf[1] + geom_max_doubles<NP>());
-        bbuf[0] = reinterpret_cast<BoxRec<NP> *>(bar + 4);      /* present only when boxes != NULL */
-        bbuf[1] = bbuf[0] + CHUNK;
+        gbuf0 = reinterpret_cast<double *>(buf0 + 2 * CHUNK);
+        bar = reinterpret_cast<uint64_t *>(gbuf0 + 2 * geom_max_doubles<NP>());
+        bbuf0 = reinterpret_cast<BoxRec<NP> *>(bar + 4);        /* present only when boxes != NULL */
         phase = 0;
         stream = static_cast<const LeafRec<NP> *>(leafrec);
         lane = lane_;
@@ -172,8 +175,8 @@ template <int NP> struct WarpStage {
             const uint32_t bytes = (uint32_t)cnt * (uint32_t)sizeof(LeafRec<NP>);
             const uint32_t bbytes = boxes ? (uint32_t)cnt * (uint32_t)sizeof(BoxRec<NP>) : 0u;
             mbar_expect_tx(bar + s, bytes + bbytes);
-            bulk_g2s(buf[s], stream + first, bytes, bar + s);
-            if (boxes) bulk_g2s(bbuf[s], boxes + first, bbytes, bar + s);
+            bulk_g2s(buf(s), stream + first, bytes, bar + s);
+            if (boxes) bulk_g2s(bbuf(s), boxes + first, bbytes, bar + s);
         }
     }
     /* lane 0 starts the copy of a geometry block (n16 16-byte units at geom[off]) into gbuf[g] */
@@ -181,7 +184,7 @@ template <int NP> struct WarpStage {
     {
         if (lane == 0 && !fault) {
             mbar_expect_tx(bar + 2 + g, n16 * 16u);
-            bulk_g2s(gbuf[g], geom + off, n16 * 16u, bar + 2 + g);
+            bulk_g2s(gbuf(g), geom + off, n16 * 16u, bar + 2 + g);
         }
     }
     /* all 32 lanes wait on the same barrier, so `fault` stays warp-uniform; once set,
@@ -336,7 +339,8 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
             ws.fetch(s ^ 1, first + (ch + 1) * CHUNK, rest < CHUNK ? rest : CHUNK);
         }
         ws.wait(s);
-        const LeafRec<NP> *rec = ws.buf[s];
+        const LeafRec<NP> *rec = ws.buf(s);
+        const BoxRec<NP> *brec = ws.bbuf(s);
 
         /* broad phase */
         unsigned cand = 0;
@@ -351,7 +355,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                     const double *rp = reinterpret_cast<const double *>(rec + k);
                     const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);    /* boxed, par_mask */
                     bool pass = true;
-                    if (bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(ws.bbuf[s][k].lo, ws.bbuf[s][k].hi, of, vif);
+                    if (bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(brec[k].lo, brec[k].hi, of, vif);
                     if (pass) {
                         double c[NP];
                         lds_vec<NP>(c, rp);
@@ -426,7 +430,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                     double dist = -1;
                     int win = id;
                     if (staged) {
-                        ret = intersect_prim<NP, false, LdShared>(sc, fo, ws.gbuf[gs], o, v, res, nrm, none);
+                        ret = intersect_prim<NP, false, LdShared>(sc, fo, ws.gbuf(gs), o, v, res, nrm, none);
                         if (ret) dist = vdist<NP>(o, res);
                     } else if (fo.type != NDT_T_HCUBE) {
                         ret = false;        /* unreachable: ndt_b200_upload refuses blocks that cannot be staged */
@@ -488,19 +492,6 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
     if (want) {
         NDT_UNROLL
         for (int i = 0; i < NP; ++i) { o_dyn[i] = o[i]; v_dyn[i] = v[i]; }
-        NDT_NO_UNROLL
-        for (int i = 0; i < NP; ++i) {
-            double vi = v_dyn[i], r;
-            if (vi < EPS2 && vi >= 0.0) r = INV_EPS2;
-            else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
-            else r = 1.0 / vi;
-            vinv[i] = r;
-            if (sc.any_boxed) {         /* the slab test wants the true reciprocal (+-inf for a zero component) */
-                obox[i] = (float)o_dyn[i];
-                vbox[i] = (float)(1.0 / vi);
-            }
-        }
-
         /* infinite objects first, linear, no mailbox (kd-tree.c:592-594) */
         md = trace_list_slow_impl<NP>(sc, sc.inf, sc.n_inf, 0, o_dyn, v_dyn, dist_limit, &out.id, &out.win);
         ret = !(md < 0);
@@ -529,6 +520,20 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
                 if ((u >= -EPS) && (l <= u)) {
                     mb.clear();
                     walking = true;
+                    /* only the rays that enter the root box (12 % in config 2) need the per-axis
+                     * reciprocals of the walk and of the box cull */
+                    NDT_NO_UNROLL
+                    for (int i = 0; i < NP; ++i) {
+                        double vi = v_dyn[i], r;
+                        if (vi < EPS2 && vi >= 0.0) r = INV_EPS2;
+                        else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
+                        else r = 1.0 / vi;
+                        vinv[i] = r;
+                        if (sc.any_boxed) {     /* the slab test wants the true reciprocal (+-inf for a zero component) */
+                            obox[i] = (float)o_dyn[i];
+                            vbox[i] = (float)(1.0 / vi);
+                        }
+                    }
                 }
             }
         }
