@@ -19,7 +19,7 @@ using namespace ndt;
 #define NDT_MIN_BLOCKS 3      /* resident CTAs per SM the register allocation is bounded for */
 #endif
 #ifndef NDT_TRACE_MIN_BLOCKS
-#define NDT_TRACE_MIN_BLOCKS 4   /* measured: 4 beats 2, 3 and 5 on config 2 */
+#define NDT_TRACE_MIN_BLOCKS 2   /* after the box cull k_trace is bound by latency on its own local memory: 255 registers (2 CTA/SM) beat 168 (3) and 128 (4): 3.48 / 3.80 / 4.49 ms on config 2 */
 #endif
 
 struct GenArgs {
