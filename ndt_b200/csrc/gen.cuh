@@ -22,6 +22,39 @@ using namespace ndt;
 #define NDT_TRACE_MIN_BLOCKS 2   /* after the box cull k_trace is bound by latency on its own local memory: 255 registers (2 CTA/SM) beat 168 (3) and 128 (4): 3.48 / 3.80 / 4.49 ms on config 2 */
 #endif
 
+/* queue entries and records move as 16-byte words: a lane's entry is 144 / 80 bytes away from its
+ * neighbour's, so 8-byte accesses touched 32 sectors per instruction and the load/store queue was the
+ * stall of k_shade (ncu: lg 14 %) */
+template <int NP>
+__device__ __forceinline__ void ray_store(RayIn<NP> *out, const double *o, const double *v, double frac, int depth)
+{
+    double2 *d = reinterpret_cast<double2 *>(out);
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) d[i / 2] = make_double2(o[i], o[i + 1]);
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) d[NP / 2 + i / 2] = make_double2(v[i], v[i + 1]);
+    d[NP] = make_double2(frac, __hiloint2double(0, depth));     /* frac | depth, pad */
+}
+template <int NP>
+__device__ __forceinline__ void ray_load(const RayIn<NP> *in, double *o, double *v, double &frac, int &depth)
+{
+    const double2 *d = reinterpret_cast<const double2 *>(in);
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) { const double2 t = d[i / 2]; o[i] = t.x; o[i + 1] = t.y; }
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) { const double2 t = d[NP / 2 + i / 2]; v[i] = t.x; v[i + 1] = t.y; }
+    const double2 t = d[NP];
+    frac = t.x;
+    depth = __double2loint(t.y);
+}
+__device__ __forceinline__ void rec_store(RayRec *dst, const RayRec &r)
+{
+    const double2 *s = reinterpret_cast<const double2 *>(&r);
+    double2 *d = reinterpret_cast<double2 *>(dst);
+    NDT_UNROLL
+    for (int i = 0; i < (int)(sizeof(RayRec) / 16); ++i) d[i] = s[i];
+}
+
 struct GenArgs {
     int gen;                 /* 0: rays are generated from pixels */
     int start, count;        /* this generation's slots are [start, start+count) */
@@ -185,23 +218,17 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
                 const int s = wbase + __popc(b1 & lt);
                 rec.child_refl = fits ? s : CHILD_BLACK;
                 if (fits) {
-                    RayIn<NP> *out = rays + (s - a.n0);
-                    NDT_UNROLL
-                    for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refl_dir[i]; }
-                    out->frac = sp.refl_frac; out->depth = depth - 1; out->pad = 0;
+                    ray_store<NP>(rays + (s - a.n0), sp.origin, sp.refl_dir, sp.refl_frac, depth - 1);
                 }
             }
             if (q2) {
                 const int s = wbase + __popc(b1) + __popc(b2 & lt);
                 rec.child_refr = fits ? s : CHILD_BLACK;
                 if (fits) {
-                    RayIn<NP> *out = rays + (s - a.n0);
-                    NDT_UNROLL
-                    for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refr_dir[i]; }
-                    out->frac = sp.refr_frac; out->depth = depth - 1; out->pad = 0;
+                    ray_store<NP>(rays + (s - a.n0), sp.origin, sp.refr_dir, sp.refr_frac, depth - 1);
                 }
             }
-            a.rec[a.start + r] = rec;
+            rec_store(a.rec + (a.start + r), rec);
             if (a.gen == 0) {
                 const size_t p = (size_t)ty * a.tw + tx;
                 if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
@@ -214,7 +241,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
             z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
             z.h[0] = z.h[1] = z.h[2] = 0.0;
             z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
-            a.rec[a.start + r] = z;
+            rec_store(a.rec + (a.start + r), z);
             if (tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
                 const size_t p = (size_t)ty * a.tw + tx;
                 if (a.out_hit) a.out_hit[p] = 0;
@@ -305,11 +332,7 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, int
         active = active && tx < a.tw && ty < a.th;
         if (active) active = primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
     } else if (active) {
-        const RayIn<NP> *in = (const RayIn<NP> *)a.rays + (a.start + r - a.n0);
-        NDT_UNROLL
-        for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
-        frac = in->frac;
-        depth = in->depth;
+        ray_load<NP>((const RayIn<NP> *)a.rays + (a.start + r - a.n0), o, v, frac, depth);
     }
     return active;
 }
@@ -350,11 +373,9 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         } else {
             want = r < count;
             if (want) {
-                const RayIn<NP> *in = (const RayIn<NP> *)a.srays + r;
-                NDT_UNROLL
-                for (int i = 0; i < NP; ++i) { o[i] = in->o[i]; v[i] = in->v[i]; }
-                limit = in->frac;
-                dir_light = in->depth - 1;
+                int code;
+                ray_load<NP>((const RayIn<NP> *)a.srays + r, o, v, limit, code);
+                dir_light = code - 1;
             }
         }
         Hit T;
@@ -385,6 +406,11 @@ const Scene sc, const WaveArgs a)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;     /* the grid covers count rounded up to whole warps */
     double o[NP], v[NP], frac;
     int depth, tx, ty;
+    /* the kernel is bound by the latency of its first loads (ncu: long_scoreboard at the first use of the
+     * hit record): start them before the ray is rebuilt */
+    HitRec h;
+    h.t = -1; h.id = -1; h.win = -1; h.found = 0; h.pad = 0;
+    if (r < a.count) h = a.hits[a.start + r];
     const bool active = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
     Tally<false> none;
     Shade<NP> S;
@@ -395,7 +421,6 @@ const Scene sc, const WaveArgs a)
     double p_dist = -1.0;
     uint32_t nsh = 0;
     if (active) {
-        const HitRec h = a.hits[a.start + r];
         Hit T;
         T.t = h.t; T.id = h.id; T.win = h.win; T.found = h.found;
         shade_setup<NP, false>(sc, S, -1, o, v, nsh, none);
@@ -419,12 +444,9 @@ const Scene sc, const WaveArgs a)
                     if (want) {
                         slot = wbase + __popc(b & ((1u << lane) - 1u));
                         if (slot < a.scap) {
-                            RayIn<NP> *out = (RayIn<NP> *)a.srays + slot;
-                            NDT_UNROLL
-                            for (int i = 0; i < NP; ++i) { out->o[i] = S.ro[i]; out->v[i] = S.rv[i]; }
-                            out->frac = S.limit;
-                            out->depth = S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0;   /* light index + 1: any-hit query */
-                            out->pad = 0;
+                            /* depth = light index + 1 for the any-hit query of a DIRECTIONAL light */
+                            ray_store<NP>((RayIn<NP> *)a.srays + slot, S.ro, S.rv, S.limit,
+                                          S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0);
                         } else {
                             atomicExch(a.ctr + 2, 1);
                             slot = -1;
@@ -472,23 +494,17 @@ const Scene sc, const WaveArgs a)
             const int s = wbase + __popc(b1 & lt);
             rec.child_refl = fits ? s : CHILD_BLACK;
             if (fits) {
-                RayIn<NP> *out = rays + (s - a.n0);
-                NDT_UNROLL
-                for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refl_dir[i]; }
-                out->frac = sp.refl_frac; out->depth = depth - 1; out->pad = 0;
+                ray_store<NP>(rays + (s - a.n0), sp.origin, sp.refl_dir, sp.refl_frac, depth - 1);
             }
         }
         if (q2) {
             const int s = wbase + __popc(b1) + __popc(b2 & lt);
             rec.child_refr = fits ? s : CHILD_BLACK;
             if (fits) {
-                RayIn<NP> *out = rays + (s - a.n0);
-                NDT_UNROLL
-                for (int i = 0; i < NP; ++i) { out->o[i] = sp.origin[i]; out->v[i] = sp.refr_dir[i]; }
-                out->frac = sp.refr_frac; out->depth = depth - 1; out->pad = 0;
+                ray_store<NP>(rays + (s - a.n0), sp.origin, sp.refr_dir, sp.refr_frac, depth - 1);
             }
         }
-        a.rec[a.start + r] = rec;
+        rec_store(a.rec + (a.start + r), rec);
         if (a.gen == 0 && !a.samples_xy) {
             const size_t p = (size_t)ty * a.tw + tx;
             if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
@@ -501,7 +517,7 @@ const Scene sc, const WaveArgs a)
         z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
         z.h[0] = z.h[1] = z.h[2] = 0.0;
         z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
-        a.rec[a.start + r] = z;
+        rec_store(a.rec + (a.start + r), z);
         if (!a.samples_xy && tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
             const size_t p = (size_t)ty * a.tw + tx;
             if (a.out_hit) a.out_hit[p] = 0;

@@ -21,7 +21,7 @@ constexpr uint32_t REC_UNTRACED = 2u;
 constexpr int CHILD_NONE = -1;
 constexpr int CHILD_BLACK = -2;   /* child cut by pixel_frac < 1/512 or depth 0 (ndt.c:336-341): colour (0,0,0), no trace */
 
-struct RayRec {
+struct alignas(16) RayRec {
     double clr[3];
     double alpha;
     double h[3];          /* get_reflect (ndt.c:383) */
