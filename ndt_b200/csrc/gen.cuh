@@ -47,6 +47,13 @@ __device__ __forceinline__ void ray_load(const RayIn<NP> *in, double *o, double 
     frac = t.x;
     depth = __double2loint(t.y);
 }
+__device__ __forceinline__ void rec_load(RayRec &r, const RayRec *src)
+{
+    const double2 *s = reinterpret_cast<const double2 *>(src);
+    double2 *d = reinterpret_cast<double2 *>(&r);
+    NDT_UNROLL
+    for (int i = 0; i < (int)(sizeof(RayRec) / 16); ++i) d[i] = s[i];
+}
 __device__ __forceinline__ void rec_store(RayRec *dst, const RayRec &r)
 {
     const double2 *s = reinterpret_cast<const double2 *>(&r);
@@ -281,10 +288,23 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
  * light loop twice (A to emit the queries, B to consume the answers): both are a few hundred
  * flops per ray against the thousands of a traversal.
  * ------------------------------------------------------------------------- */
-struct HitRec {
+struct alignas(16) HitRec {
     double t;
     int32_t id, win, found, pad;
-};                            /* 24 bytes */
+    double pad2;
+};                            /* 32 bytes = two 16-byte words */
+__device__ __forceinline__ void hit_store(HitRec *dst, double t, int id, int win, int found)
+{
+    double2 *d = reinterpret_cast<double2 *>(dst);
+    d[0] = make_double2(t, __hiloint2double(win, id));
+    d[1] = make_double2(__hiloint2double(0, found), 0.0);
+}
+__device__ __forceinline__ void hit_load(const HitRec *src, double &t, int &id, int &win, int &found)
+{
+    const double2 *s = reinterpret_cast<const double2 *>(src);
+    const double2 a = s[0], b = s[1];
+    t = a.x; id = __double2loint(a.y); win = __double2hiint(a.y); found = __double2loint(b.x);
+}
 
 struct WaveArgs {
     int gen;                 /* 0: rays are generated from pixels */
@@ -381,12 +401,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         Hit T;
         trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
         if (ws.fault) break;     /* warp-uniform (warp.cuh) */
-        if (want) {
-            HitRec h;
-            h.t = T.t; h.id = T.id; h.win = T.win; h.found = T.found; h.pad = 0;
-            if (MODE == 0) a.hits[a.start + r] = h;
-            else a.shits[r] = h;
-        }
+        if (want) hit_store(MODE == 0 ? a.hits + (a.start + r) : a.shits + r, T.t, T.id, T.win, T.found);
     }
     if (kd_overflow) atomicMax(a.ctr + 3, 1);
     if (ws.fault) atomicMax(a.ctr + 3, 2);
@@ -408,9 +423,9 @@ const Scene sc, const WaveArgs a)
     int depth, tx, ty;
     /* the kernel is bound by the latency of its first loads (ncu: long_scoreboard at the first use of the
      * hit record): start them before the ray is rebuilt */
-    HitRec h;
-    h.t = -1; h.id = -1; h.win = -1; h.found = 0; h.pad = 0;
-    if (r < a.count) h = a.hits[a.start + r];
+    Hit T0;
+    T0.t = -1; T0.id = -1; T0.win = -1; T0.found = 0;
+    if (r < a.count) hit_load(a.hits + (a.start + r), T0.t, T0.id, T0.win, T0.found);
     const bool active = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
     Tally<false> none;
     Shade<NP> S;
@@ -421,10 +436,8 @@ const Scene sc, const WaveArgs a)
     double p_dist = -1.0;
     uint32_t nsh = 0;
     if (active) {
-        Hit T;
-        T.t = h.t; T.id = h.id; T.win = h.win; T.found = h.found;
         shade_setup<NP, false>(sc, S, -1, o, v, nsh, none);
-        shade_after<NP, false>(sc, S, -1, T, o, v, rec, p_hit, p_id, p_dist, none);
+        shade_after<NP, false>(sc, S, -1, T0, o, v, rec, p_hit, p_id, p_dist, none);
     }
     const int nl = sc.n_lights;
     if (__ballot_sync(FULL, active && S.shaded)) {
@@ -458,10 +471,7 @@ const Scene sc, const WaveArgs a)
                 const int slot = a.sslot[(size_t)r * nl + it];
                 Hit T;
                 T.t = -1; T.id = -1; T.win = -1; T.found = 0;
-                if (slot >= 0) {
-                    const HitRec h = a.shits[slot];
-                    T.t = h.t; T.id = h.id; T.win = h.win; T.found = h.found;
-                }
+                if (slot >= 0) hit_load(a.shits + slot, T.t, T.id, T.win, T.found);
                 shade_after<NP, false>(sc, S, it, T, o, v, rec, p_hit, p_id, p_dist, none);
             }
         }

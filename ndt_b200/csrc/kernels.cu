@@ -55,12 +55,13 @@ __global__ void k_resolve(RayRec *rec, int start, int count, int specular)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    RayRec r = rec[start + i];
+    RayRec r;
+    rec_load(r, rec + start + i);
     if (r.child_refl == CHILD_NONE && r.child_refr == CHILD_NONE) return;
     const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
     const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
     resolve_rec(r, c1, c2, specular);
-    rec[start + i] = r;
+    rec_store(rec + start + i, r);
 }
 
 /* generation 0 -> pixels */
@@ -73,7 +74,8 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
         const int tx = p % tw, ty = p / tw;
         /* bpr == 0: a sample list, record r belongs to sample r */
         const int slot = bpr ? ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7) : p;
-        RayRec r = rec[slot];
+        RayRec r;
+        rec_load(r, rec + slot);
         const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
         const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
         resolve_rec(r, c1, c2, specular);
