@@ -183,6 +183,14 @@ void ndt_b200_host_free(void *p);
  * a negative status. */
 int ndt_b200_kd_tree_build(void *kd_tree, void *kd_item_list);
 
+/* The same exhaustive plane search with a bounded recursion, for scenes the reference's builder does
+ * not finish (scenes/random.c beyond a few hundred objects: every plane is straddled by many objects,
+ * both sides keep them, kd-tree.c:381-403 recurses on ever larger lists).  Stops at max_depth, at
+ * leaf_size items, and where a split would grow the reference count by more than max_growth (> 1).
+ * Same kd_tree_t as output; not the tree the reference would build, so hit / id parity is checked
+ * against the reference's tree-less trace() (object.c:692) instead of its kd result. */
+int ndt_b200_kd_tree_build_bounded(void *kd_tree, void *kd_item_list, int max_depth, int leaf_size, double max_growth);
+
 /* trace_kd (object.c:683) for n_rays explicit rays: origins/dirs are n_rays x N
  * doubles (row-major, HOST), dist_limits may be NULL (= -1.0, "check all
  * objects", ndt.c:172-183).  Outputs per ray: trace_kd's return value, the id

@@ -197,6 +197,13 @@ def kd_tree_build(kd_tree_ptr, kd_item_list_ptr):
     return _check(lib().ndt_b200_kd_tree_build(kd_tree_ptr, kd_item_list_ptr))
 
 
+def kd_tree_build_bounded(kd_tree_ptr, kd_item_list_ptr, max_depth=16, leaf_size=64, max_growth=1.5):
+    """ndt_b200_kd_tree_build_bounded: bounded-depth variant for scenes the reference's builder cannot finish."""
+    L = lib()
+    L.ndt_b200_kd_tree_build_bounded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double]
+    return _check(L.ndt_b200_kd_tree_build_bounded(kd_tree_ptr, kd_item_list_ptr, max_depth, leaf_size, max_growth))
+
+
 def pinned_empty(shape, dtype):
     """numpy array over page-locked host memory (ndt_b200_host_alloc); freed with the array."""
     dt = np.dtype(dtype)

@@ -123,6 +123,9 @@ struct Builder {
     cudaStream_t st;
     int gpu_nodes, host_nodes, total_nodes;
     const char *err;
+    /* ndt_b200_kd_tree_build_bounded: 0 / 0 / 0 = the reference's unbounded recursion */
+    int max_depth, leaf_size;
+    double max_growth;       /* a split whose two sides hold more than max_growth * n references is not made */
 };
 
 /* the reference's search on the host, same comparisons (small nodes) */
@@ -176,15 +179,30 @@ static bool gpu_search(Builder &B, const int *list, int n, int *out_dim, double 
 }
 
 /* kd_tree_split_node, kd-tree.c:315-419 */
-static int split_node(Builder &B, ndtabi_kd_node *node, const int *list, int n)
+static int split_node(Builder &B, ndtabi_kd_node *node, const int *list, int n, int depth = 0)
 {
     ++B.total_nodes;
     int split_dim = node->dim;
     double split_pos = 0.0;
-    bool found;
-    if (n >= KD_GPU_MIN_ITEMS) { found = gpu_search(B, list, n, &split_dim, &split_pos); ++B.gpu_nodes; }
-    else { found = host_search(B, list, n, &split_dim, &split_pos); ++B.host_nodes; }
+    bool found = false;
+    const bool stop = (B.max_depth > 0 && depth >= B.max_depth) || (B.leaf_size > 0 && n <= B.leaf_size);
+    if (!stop) {
+        if (n >= KD_GPU_MIN_ITEMS) { found = gpu_search(B, list, n, &split_dim, &split_pos); ++B.gpu_nodes; }
+        else { found = host_search(B, list, n, &split_dim, &split_pos); ++B.host_nodes; }
+    }
     if (B.err) return -1;
+    if (found && B.max_growth > 0.0) {
+        /* bounded build: overlapping objects straddle every plane; do not split when the two sides
+         * together would hold more than max_growth * n references (the reference's builder does, and
+         * never finishes on scenes like random.c with a few hundred objects: SURVEY note 8) */
+        const double *lo = B.h_lo + (size_t)split_dim * B.n_total, *hi = B.h_hi + (size_t)split_dim * B.n_total;
+        long both = 0;
+        for (int i = 0; i < n; ++i) {
+            const double il = lo[list[i]], iu = hi[list[i]];
+            if (!(iu < split_pos - EPS) && !(il > split_pos + EPS)) ++both;
+        }
+        if ((double)(n + both) > B.max_growth * (double)n) found = false;
+    }
     if (!found) {   /* leaf, kd-tree.c:360-375 */
         node->num = n;
         node->dim = -1;
@@ -219,14 +237,34 @@ static int split_node(Builder &B, ndtabi_kd_node *node, const int *list, int n)
     node->right->dim = (node->dim + 1) % B.dims;
     int rc = 0;
     if (nl > 0 && nr > 0) {
-        if (split_node(B, node->left, l, nl) < 0) rc = -1;
-        if (rc == 0 && split_node(B, node->right, r, nr) < 0) rc = -1;
+        if (split_node(B, node->left, l, nl, depth + 1) < 0) rc = -1;
+        if (rc == 0 && split_node(B, node->right, r, nr, depth + 1) < 0) rc = -1;
     }
     free(l); free(r);
     return rc;
 }
 
+static int kd_build(void *tree_v, void *items_v, int max_depth, int leaf_size, double max_growth);
+
 extern "C" int ndt_b200_kd_tree_build(void *tree_v, void *items_v)
+{
+    return kd_build(tree_v, items_v, 0, 0, 0.0);
+}
+
+/* The same search (every candidate plane scored on the GPU, kd-tree.c:294-345) with a bounded
+ * recursion, for scenes the reference's builder cannot finish (note 8): stops at
+ * max_depth, at leaf_size items, and wherever a split would grow the number of references by more than
+ * max_growth.  The tree is a valid kd_tree_t for kd_tree_intersect / ndt_b200_flatten; it is NOT the
+ * tree the reference would build (it cannot build one), so results are checked against the reference's
+ * tree-less trace() instead. */
+extern "C" int ndt_b200_kd_tree_build_bounded(void *tree_v, void *items_v, int max_depth, int leaf_size, double max_growth)
+{
+    if (max_depth < 1 || leaf_size < 1 || !(max_growth > 1.0))
+        return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_kd_tree_build_bounded: max_depth >= 1, leaf_size >= 1, max_growth > 1");
+    return kd_build(tree_v, items_v, max_depth, leaf_size, max_growth);
+}
+
+static int kd_build(void *tree_v, void *items_v, int max_depth, int leaf_size, double max_growth)
 {
     ndtabi_kd_tree *tree = (ndtabi_kd_tree *)tree_v;
     kdb_item_list *items = (kdb_item_list *)items_v;
@@ -250,6 +288,7 @@ extern "C" int ndt_b200_kd_tree_build(void *tree_v, void *items_v)
     Builder B;
     memset(&B, 0, sizeof B);
     B.dims = dims; B.n_total = n; B.items = items->items;
+    B.max_depth = max_depth; B.leaf_size = leaf_size; B.max_growth = max_growth;
     B.h_lo = (double *)malloc((size_t)dims * (n ? n : 1) * sizeof(double));
     B.h_hi = (double *)malloc((size_t)dims * (n ? n : 1) * sizeof(double));
     int *root_list = (int *)malloc((size_t)(n ? n : 1) * sizeof(int));

@@ -163,6 +163,39 @@ int refh_skip_frame(int dims, int frame, int frames, const char *cfg)
     return 0;
 }
 
+static int g_skip_kd_build = 0;
+/* the same without kd_tree_build: the global kd-tree is initialised and left empty, to be built by
+ * ndt_b200_kd_tree_build_bounded (scenes the reference's exhaustive builder cannot finish, SURVEY note 8) */
+int refh_begin_frame_nokd(int dims, int frame, int frames, const char *cfg)
+{
+    g_skip_kd_build = 1;
+    int r = refh_begin_frame(dims, frame, frames, cfg, NULL);
+    g_skip_kd_build = 0;
+    return r;
+}
+
+/* trace() (object.c:692) over ALL kd items, no mask, no tree: the brute-force answer the kd result is
+ * checked against.  Returns trace()'s return value; *obj_id = kd item index of the reported object or -1 */
+int refh_trace_brute(const double *o, const double *v, double dist_limit, double *hit_out, int *obj_id)
+{
+    if (!g_frame_open)
+        return -1;
+    int dim = g_scn.dimensions;
+    vectNd pos, look, hp, hn;
+    vectNd_calloc(&pos, dim); vectNd_calloc(&look, dim); vectNd_calloc(&hp, dim); vectNd_calloc(&hn, dim);
+    for (int i = 0; i < dim; ++i) { vectNd_set(&pos, i, o[i]); vectNd_set(&look, i, v[i]); }
+    object *ptr = NULL;
+    int r = trace(&pos, &look, g_flat, NULL, g_nflat, NULL, &hp, &hn, &ptr, NULL, dist_limit);
+    *obj_id = -1;
+    if (ptr)
+        for (int i = 0; i < g_nflat; ++i)
+            if (g_flat[i] == ptr) { *obj_id = i; break; }
+    if (hit_out)
+        for (int i = 0; i < dim; ++i) hit_out[i] = hp.v[i];
+    vectNd_free(&pos); vectNd_free(&look); vectNd_free(&hp); vectNd_free(&hn);
+    return r;
+}
+
 int refh_begin_frame(int dims, int frame, int frames, const char *cfg, double *kd_seconds)
 {
     if (g_frame_open)
@@ -181,7 +214,8 @@ int refh_begin_frame(int dims, int frame, int frames, const char *cfg, double *k
         object_kdlist_add(&g_items, o, i);
         flat_add(o);
     }
-    kd_tree_build(&kdtree, &g_items);
+    if (!g_skip_kd_build)
+        kd_tree_build(&kdtree, &g_items);
     clock_gettime(CLOCK_MONOTONIC, &b);
     if (kd_seconds)
         *kd_seconds = (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);

@@ -51,6 +51,8 @@ class RefHarness:
         L.refh_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.refh_render_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.refh_render_aa.argtypes = [C.c_int] * 6 + [C.c_void_p, C.POINTER(C.c_double)]
+        L.refh_begin_frame_nokd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.refh_trace_brute.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int)]
         L.refh_set_camera.argtypes = [C.c_int, C.c_double, C.c_double]
         L.refh_rotate2_ptr.restype = C.c_void_p
         L.refh_primary.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -96,6 +98,19 @@ class RefHarness:
         self._next_frame = frame + 1
         self.kd_seconds = kd.value
         self.dims = dims
+
+    def begin_frame_nokd(self, dims, frame, frames, cfg=None):
+        """begin_frame without kd_tree_build: the global tree is left for ndt_b200.kd_tree_build_bounded."""
+        r = self.lib.refh_begin_frame_nokd(dims, frame, frames, cfg.encode() if cfg else None)
+        if r != 0:
+            raise RuntimeError(f"refh_begin_frame_nokd -> {r}")
+
+    def trace_brute(self, o, v, dist_limit=-1.0):
+        """trace() over every kd item without a tree (object.c:692): (return value, hit point, item id)."""
+        o = np.ascontiguousarray(o, np.float64); v = np.ascontiguousarray(v, np.float64)
+        hit = np.zeros_like(o); oid = C.c_int(-1)
+        r = self.lib.refh_trace_brute(o.ctypes.data, v.ctypes.data, dist_limit, hit.ctypes.data, C.byref(oid))
+        return r, hit, oid.value
 
     def end_frame(self):
         self.lib.refh_end_frame()

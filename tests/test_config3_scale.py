@@ -1,0 +1,94 @@
+"""BASELINE config 3 (scenes/random.c, 6-D, thousands of overlapping spheres / orthotopes) at a size the
+reference's kd builder cannot finish (SURVEY note 8, section 8d): the tree comes from
+ndt_b200_kd_tree_build_bounded -- a valid kd_tree_t in host memory -- and the device must answer every
+query exactly like the reference's own trace_kd (object.c:683) walking THAT tree.  How often that
+answer differs from the reference's tree-less trace() (object.c:692) over all objects is reported too:
+kd_tree_intersect prunes with *t_ptr and per-leaf EPSILON hysteresis, so for rays that start inside
+the cloud the two reference code paths do not agree with each other either (not a device property)."""
+import time
+
+import numpy as np
+import pytest
+
+import ndt_b200
+
+pytestmark = pytest.mark.gpu
+N_OBJECTS = 1500
+W, H = 160, 90
+
+
+def primary_rays(flat, step):
+    """(o, v) of every step-th pixel, camera.c:557-575 on the flat scene's camera block."""
+    h = flat.header
+    n, npad = h.n, h.npad
+    cam = np.frombuffer(flat.blob, np.float64, 4 * npad, h.off_camera).reshape(4, npad)[:, :n]
+    pos, orig, dx, dy = cam
+    rays_o, rays_v, pix = [], [], []
+    for j in range(0, h.height, step):
+        for i in range(0, h.width, step):
+            x = i / h.width - 0.5
+            y = -(j / h.height - 0.5)
+            p = orig + dx * x + dy * y
+            if h.use_focal:
+                p = pos + (p - pos) * h.focal_scale
+            v = p - pos
+            rays_o.append(pos.copy()); rays_v.append(v / np.sqrt((v * v).sum())); pix.append((j, i))
+    return np.array(rays_o), np.array(rays_v), pix
+
+
+@pytest.mark.parametrize("growth", [1.5, 1.95])
+def test_random_scene_with_a_bounded_tree_against_brute_force(ref, growth):
+    ref.open_scene("random")
+    t0 = time.perf_counter()
+    ref.begin_frame_nokd(6, 0, 300, str(N_OBJECTS))
+    t_scene = time.perf_counter() - t0
+    try:
+        t0 = time.perf_counter()
+        rc = ndt_b200.kd_tree_build_bounded(ref.kdtree_ptr, ref.items_ptr, max_depth=14, leaf_size=48, max_growth=growth)
+        t_kd = time.perf_counter() - t0
+        assert rc in (0, 1)
+        flat = ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, W, H, 128, 1, ref.get_bounds_ptr)
+        hd = flat.header
+        assert hd.n_items == N_OBJECTS
+        o, v, pix = primary_rays(flat, 3)
+        n_prim = len(o)
+        # the camera of random.c sees little of the cloud (its 6-D objects rarely cut the 3-D view): add rays
+        # aimed at the objects, from the camera and from inside the cloud
+        rng = np.random.default_rng(3)
+        bs = np.frombuffer(flat.blob, np.float64, hd.n_objects * (hd.npad + 2), hd.off_bspheres).reshape(hd.n_objects, hd.npad + 2)
+        cam_pos = o[0].copy()
+        eo, ev = [], []
+        for k in range(1500):
+            i = rng.integers(hd.n_items)
+            src = cam_pos if k % 2 == 0 else rng.uniform(2.0, 12.0, size=hd.n)
+            tgt = bs[i, :hd.n] + rng.normal(size=hd.n) * abs(bs[i, hd.npad]) * 0.4
+            d = tgt - src
+            eo.append(src.copy()); ev.append(d / np.sqrt((d * d).sum()))
+        o = np.vstack([o, np.array(eo)]); v = np.vstack([v, np.array(ev)])
+        brute = [ref.trace_brute(o[k], v[k]) for k in range(len(o))]
+        kd = [ref.trace_ray(o[k], v[k]) for k in range(len(o))]       # trace_kd on the bounded tree
+    finally:
+        ref.end_frame()
+    with ndt_b200.Context(0) as ctx:
+        ctx.upload(flat)
+        frame = ctx.render_tile(0, 0, W, H)
+        found, oid, t, hit, nrm = ctx.trace_rays(o, v)
+    want_id = np.array([k_[3] for k_ in kd])
+    want_found = np.array([1 if k_[0] else 0 for k_ in kd])
+    diff = np.flatnonzero((oid != want_id) | ((found != 0) != (want_found != 0)))
+    same = np.flatnonzero((oid == want_id) & (oid >= 0))
+    hit_err = max((float(np.abs(hit[k] - kd[k][1]).max()) for k in same), default=0.0)
+    brute_id = np.array([b[2] for b in brute])
+    kd_vs_brute = int((brute_id != want_id).sum())
+    n_hits = int((want_id >= 0).sum())
+    print(f"\\nrandom.c 6-D, {N_OBJECTS} objects, max_growth {growth}: scene + bounds {t_scene:.1f} s, bounded kd build {t_kd*1e3:.0f} ms "
+          f"({hd.n_nodes} nodes, {hd.n_leaf_refs} leaf refs, largest leaf {hd.max_leaf}, depth {hd.tree_depth}); "
+          f"{len(o)} rays ({n_hits} hit something): {len(diff)} differ from the reference's trace_kd on the same tree, hit points within {hit_err:.2e}; "
+          f"the reference's trace_kd and its tree-less trace() disagree on {kd_vs_brute}; "
+          f"frame {W}x{H}: {frame.stats.rays_unique} rays in {frame.stats.device_ms:.2f} ms")
+    assert len(diff) == 0, (len(diff), len(o))
+    assert hit_err == 0.0
+    # the frame's primary-ray buffers agree with the probe
+    got_id = np.array([frame.obj_id[j, i] for j, i in pix])
+    assert np.array_equal(got_id, oid[:n_prim])
+    assert n_hits > 500
