@@ -163,6 +163,31 @@ int refh_skip_frame(int dims, int frame, int frames, const char *cfg)
     return 0;
 }
 
+/* `ndt -y` (ndt.c:1798-1808): scene_setup for the frame, then the reference's own scene_write_yaml
+ * (scene.c:1000) -- before kd build and camera_aim, so nothing "prepared" is dumped.  to_buffer != 0 goes
+ * through scene_write_yaml_buffer (scene.c:1045, the MPI scene transport) and then writes that text. */
+int refh_write_yaml(int dims, int frame, int frames, const char *cfg, const char *fname, int to_buffer)
+{
+    int r;
+    if (g_frame_open)
+        return -1;
+    hush(1);
+    g_setup(&g_scn, dims, frame, frames, (char *)cfg);
+    if (to_buffer) {
+        unsigned char *buf = NULL;
+        size_t len = 0;
+        r = scene_write_yaml_buffer(&g_scn, &buf, &len);
+        FILE *fp = fopen(fname, "wb");
+        if (!fp || fwrite(buf, 1, len, fp) != len) r = -2;
+        if (fp) fclose(fp);
+        free(buf);
+    } else
+        r = scene_write_yaml(&g_scn, (char *)fname);
+    scene_free(&g_scn);
+    hush(0);
+    return r;
+}
+
 static int g_skip_kd_build = 0;
 /* the same without kd_tree_build: the global kd-tree is initialised and left empty, to be built by
  * ndt_b200_kd_tree_build_bounded (scenes the reference's exhaustive builder cannot finish, SURVEY note 8) */

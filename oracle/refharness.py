@@ -51,6 +51,7 @@ class RefHarness:
         L.refh_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.refh_render_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.refh_render_aa.argtypes = [C.c_int] * 6 + [C.c_void_p, C.POINTER(C.c_double)]
+        L.refh_write_yaml.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
         L.refh_begin_frame_nokd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.refh_trace_brute.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int)]
         L.refh_set_camera.argtypes = [C.c_int, C.c_double, C.c_double]
@@ -80,12 +81,20 @@ class RefHarness:
         self._scene = scene or ""
         self._next_frame = 0
 
+    def _cfg(self, cfg):
+        """scenes/yaml.c takes a file name as its config string: repo-relative names are resolved here"""
+        if cfg and self._scene == "yaml" and not os.path.isabs(cfg):
+            cfg = os.path.join(os.path.dirname(HERE), cfg)
+        return cfg
+
     def scene_frames(self, dims, cfg=None):
+        cfg = self._cfg(cfg)
         return self.lib.refh_scene_frames(dims, cfg.encode() if cfg else None)
 
     def begin_frame(self, dims, frame, frames, cfg=None):
         """scene_setup(frame) + kd build + camera_aim.  Stateful scenes (balls.c)
         need every earlier frame's scene_setup to have run, in order."""
+        cfg = self._cfg(cfg)
         cfgb = cfg.encode() if cfg else None
         if frame < self._next_frame:
             self.open_scene(self._scene)  # restart the plugin's state
@@ -98,6 +107,17 @@ class RefHarness:
         self._next_frame = frame + 1
         self.kd_seconds = kd.value
         self.dims = dims
+
+    def write_yaml(self, dims, frame, frames, fname, cfg=None, to_buffer=False):
+        """scene_setup(frame) + the reference's scene_write_yaml / scene_write_yaml_buffer (ndt -y, ndt.c:1798-1808)"""
+        if frame < self._next_frame:
+            self.open_scene(self._scene)
+        for f in range(self._next_frame, frame):
+            self.lib.refh_skip_frame(dims, f, frames, cfg.encode() if cfg else None)
+        r = self.lib.refh_write_yaml(dims, frame, frames, cfg.encode() if cfg else None, fname.encode(), int(to_buffer))
+        self._next_frame = frame + 1
+        if r != 0:
+            raise RuntimeError(f"refh_write_yaml -> {r}")
 
     def begin_frame_nokd(self, dims, frame, frames, cfg=None):
         """begin_frame without kd_tree_build: the global tree is left for ndt_b200.kd_tree_build_bounded."""

@@ -6,7 +6,7 @@ string (-u), the frame, and a SMALL frame size at which the CPU oracle
 finishes in about a second.  `cfg` rows map to BASELINE.json configs:
   config1  ./ndt -d 4            config2  hypercube -d 8
   config3  random -d 6 (n=40, the reference kd builder explodes beyond ~200)
-  config4  balls -d 5            config5  mixed10d (our C twin of the 10-D YAML)
+  config4  balls -d 5            config5  mixed10d (our C twin of the 10-D YAML) and the YAML itself
 """
 import math
 from collections import namedtuple
@@ -29,6 +29,12 @@ CASES = [
     Case("config5_mixed10d", "mixed10d", 10, None, 0, 96, 54),
     Case("mixed7d", "mixed10d", 7, None, 5, 96, 54),
     Case("mixed12d", "mixed10d", 12, None, 11, 64, 36),
+    # SURVEY 8(f) rank 3, BASELINE config 5 as written: scenes loaded by the reference's scenes/yaml.c +
+    # scene_read_yaml (scene.c:2090) over include/yaml_lite; cfg = the YAML file (-u), repo-relative.
+    # config5_mixed10d.yaml is what `ndt -s mixed10d.so -d 10 -y` writes (scene_write_yaml, scene.c:1000);
+    # handwritten4d.yaml is a 3-document (3-frame) file in README.md:292-431 style, frame 1 rendered.
+    Case("config5_yaml10d", "yaml", 10, "tests/scenes/config5_mixed10d.yaml", 0, 96, 54),
+    Case("yaml_handwritten4d", "yaml", 4, "tests/scenes/handwritten4d.yaml", 1, 96, 54),
 ]
 # the other cameras and the stereo modes of render_pixel, same scenes
 VIEW_CASES = [
