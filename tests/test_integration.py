@@ -50,3 +50,14 @@ def test_stock_command_line_with_recursive_aa(tmp_path, oracle_lib):
     assert oracle_lib.ndo_render_aa(flat.blob, os.cpu_count(), 20, 4, want.ctypes.data, None, None) == 0
     d = np.abs(got.astype(np.int16) - want[..., :3].astype(np.int16))
     assert float((d <= 1).mean()) >= 0.999
+
+
+def test_stock_command_line_loads_a_yaml_scene(tmp_path, oracle_lib):
+    """`ndt -s scenes/yaml.so -u file.yaml -d 10` (README.md:423-430 of the reference; BASELINE config 5):
+    scenes/yaml.c + scene_read_yaml run unmodified over yaml_lite, the frame comes from the GPU."""
+    got = run_demo(tmp_path, "-s", os.path.join(ROOT, "oracle", "_ref", "scenes", "yaml.so"),
+                   "-u", os.path.join(ROOT, "tests", "scenes", "config5_mixed10d.yaml"),
+                   "-d", "10", "-f", "0", "-r", "96x54")
+    want = oracle_render(oracle_lib, load_flat("config5_yaml10d")).u8[..., :3]
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert float((d <= 1).mean()) >= 0.999
