@@ -55,6 +55,10 @@ WORKLOADS = {
                 "BASELINE config 4: scenes/balls.c -d 5, 4K, frame 2", "balls", 5, None, 2),
     "config5": ("config5_mixed10d", 1920, 1080,
                 "BASELINE config 5 (C twin): mixed10d -d 10, 1920x1080, frame 0", "mixed10d", 10, None, 0),
+    "config5_yaml": ("config5_yaml10d", 1920, 1080,
+                     "BASELINE config 5: scenes/yaml.c -u tests/scenes/config5_mixed10d.yaml -d 10, 1920x1080 "
+                     "(hplane, hcylinder, hdisk, hfacet; 6 lights, shadow rays), loaded by the reference's "
+                     "scene_read_yaml over yaml_lite", "yaml", 10, "tests/scenes/config5_mixed10d.yaml", 0),
 }
 FRAMES_PER_GPU = 4
 TILES_PER_FRAME = 1

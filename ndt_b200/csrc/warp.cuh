@@ -96,7 +96,7 @@ __host__ __device__ inline int geom_block_doubles(int type, int m, int np)
 template <int NP> __host__ __device__ constexpr int warp_smem_bytes(bool boxed)
 {
     return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 2 * geom_max_doubles<NP>() * 8 + 32 +
-           (boxed ? 2 * CHUNK * (int)sizeof(BoxRec<NP>) : 0);
+           (boxed ? 2 * CHUNK * (int)sizeof(BoxRec<NP>) + NP * 16 : 0);     /* + the ray bundle's bounds */
 }
 
 /* ---- mbarrier + TMA bulk copy (PTX ISA: cp.async.bulk, mbarrier) ------------- */
@@ -136,6 +136,7 @@ template <int NP> struct WarpStage {
      * (ncu: long_scoreboard on exactly those lines) */
     LeafRec<NP> *buf0;    /* two chunks of CHUNK records */
     BoxRec<NP> *bbuf0;    /* the chunks' boxes (only present / filled when boxes != NULL) */
+    float4 *bundle;       /* per axis: (min o, max o, min 1/v, max 1/v) over the warp's walking rays (bundle cull) */
     double *gbuf0;        /* two staged geometry blocks of geom_max_doubles<NP>() */
     uint64_t *bar;        /* bar[0..1]: record chunks, bar[2..3]: geometry blocks */
     __device__ __forceinline__ LeafRec<NP> *buf(int s) const { return buf0 + s * CHUNK; }
@@ -154,6 +155,7 @@ template <int NP> struct WarpStage {
         gbuf0 = reinterpret_cast<double *>(buf0 + 2 * CHUNK);
         bar = reinterpret_cast<uint64_t *>(gbuf0 + 2 * geom_max_doubles<NP>());
         bbuf0 = reinterpret_cast<BoxRec<NP> *>(bar + 4);        /* present only when boxes != NULL */
+        bundle = reinterpret_cast<float4 *>(bbuf0 + 2 * CHUNK); /* likewise */
         phase = 0;
         stream = static_cast<const LeafRec<NP> *>(leafrec);
         lane = lane_;
@@ -246,6 +248,43 @@ template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const
     /* one more ulp-scale allowance on the comparison itself */
     return tmin <= tmax * 1.000001f + 1e-30f;
 }
+
+/* BUNDLE CULL: box_hit for all rays of the warp at once, one RECORD per lane instead of one ray per lane.
+ * The 32 rays of a warp are neighbours (an 8x4 pixel block, or queue neighbours spawned by one), 99 % of a
+ * leaf's boxes are missed by each of them, and mostly by all of them: per axis the bundle is described by the
+ * intervals [o_lo, o_hi] and [vi_lo, vi_hi] of its origins and reciprocal directions (trace_kd_warp), and a
+ * record is dropped for the whole warp when the interval version of the slab test already fails.
+ * Exactness: the bounds below are built from the SAME fp32 operations as box_hit applied to interval end
+ * points; IEEE rounding is monotone, so tmin_lb <= every ray's computed tmin and tmax_ub >= every ray's
+ * computed tmax: a record dropped here would have failed box_hit for every ray of the bundle (the per-ray
+ * result is unchanged, bit for bit).  Axes on which the rays do not all run the same way (or some are
+ * parallel and some not) give no constraint; if all are parallel (1/v = +-inf, box_hit's inf arithmetic)
+ * the record is dropped when every origin lies outside the slab. */
+template <int NP> __device__ __forceinline__ bool bundle_hit(const float *lo, const float *hi, const float4 *bd)
+{
+    float tmin = 0.0f, tmax = FLT_MAX;
+    bool outside = false;
+    NDT_UNROLL
+    for (int i = 0; i < NP; ++i) {
+        const float4 b = bd[i];                         /* o_lo, o_hi, vi_lo, vi_hi: warp-uniform */
+        const float l = lo[i], h = hi[i];
+        if (b.z > 0.0f && b.w < FLT_MAX) {              /* all rays go up this axis: near = (l-o) vi, far = (h-o) vi */
+            const float a = __fsub_rn(l, b.y), d = __fsub_rn(h, b.x);
+            tmin = fmaxf(tmin, fminf(__fmul_rn(a, b.z), __fmul_rn(a, b.w)));
+            tmax = fminf(tmax, fmaxf(__fmul_rn(d, b.z), __fmul_rn(d, b.w)));
+        } else if (b.w < 0.0f && b.z > -FLT_MAX) {      /* all go down: near = (h-o) vi, far = (l-o) vi */
+            const float a = __fsub_rn(l, b.y), d = __fsub_rn(h, b.x);
+            tmin = fmaxf(tmin, fminf(__fmul_rn(d, b.z), __fmul_rn(d, b.w)));
+            tmax = fminf(tmax, fmaxf(__fmul_rn(a, b.z), __fmul_rn(a, b.w)));
+        } else if (b.z == b.w && (b.z > FLT_MAX || b.z < -FLT_MAX)) {   /* all parallel to the slab */
+            if (b.x > h || b.y < l) outside = true;
+        }
+    }
+    return !outside && tmin <= tmax * 1.000001f + 1e-30f;
+}
+/* order-preserving float <-> int, for redux.sync (integer only) */
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
 /* the ray-only half of bounding.c:34-85: desc = (v.oc)^2 - |oc|^2 + r^2 */
 template <int NP> __device__ __forceinline__ bool bsphere_ray_part(const double *c, double r2, const double *o, const double *v)
@@ -344,6 +383,20 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
 
         /* broad phase */
         unsigned cand = 0;
+        unsigned surv = cnt >= 32 ? ~0u : (1u << cnt) - 1u;
+#ifndef NDT_NO_BUNDLE_CULL
+        if (ws.boxes) {
+            /* bundle cull, all 32 lanes: lane k tests record k against the warp's ray bundle */
+            const uint32_t kmw = __reduce_or_sync(FULL, live ? keep_mask : 0u);
+            bool keep = false;
+            if (ws.lane < cnt) {
+                const double *rp = reinterpret_cast<const double *>(rec + ws.lane);
+                const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);        /* boxed, par_mask */
+                keep = !(bx.x && !(bx.y & kmw)) || bundle_hit<NP>(brec[ws.lane].lo, brec[ws.lane].hi, ws.bundle);
+            }
+            surv = __ballot_sync(FULL, keep);
+        }
+#endif
         if (live) {
             if (ws.boxes) {
                 /* boxed scene: the fp32 slab test first, the sphere test for what is left */
@@ -351,7 +404,8 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                 NDT_UNROLL
                 for (int i = 0; i < NP; ++i) { of[i] = obox[i]; vif[i] = vbox[i]; }
                 NDT_BROAD_LOOP
-                for (int k = 0; k < cnt; ++k) {
+                for (unsigned sm = surv; sm; sm &= sm - 1) {
+                    const int k = __ffs(sm) - 1;
                     const double *rp = reinterpret_cast<const double *>(rec + k);
                     const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);    /* boxed, par_mask */
                     bool pass = true;
@@ -505,8 +559,8 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             for (int i = 0; i < sc.n && !behind; ++i) {
                 const double vi = v_dyn[i], oi = o_dyn[i];
                 if (!(fabs(vi) < EPS2)) {
-                    double a = (NDT_LDG(lo + i) - oi) / vi;
-                    double b = (NDT_LDG(hi + i) - oi) / vi;
+                    double a, b;        /* both bounds over the same v_i: one reciprocal (div2_by_norm, bit-exact) */
+                    div2_by_norm(NDT_LDG(lo + i) - oi, NDT_LDG(hi + i) - oi, vi, a, b);
                     if (a > b) { double x = a; a = b; b = x; }
                     if (a > l) l = a;
                     if (b < u) u = b;
@@ -538,6 +592,23 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             }
         }
     }
+
+#ifndef NDT_NO_BUNDLE_CULL
+    /* the bundle of the rays that walk the tree (see bundle_hit): per axis the extremes of origin and
+     * reciprocal direction, 4 NP integer reductions per 32 rays, kept in shared memory */
+    if (sc.any_boxed && __ballot_sync(FULL, walking)) {
+        NDT_NO_UNROLL
+        for (int i = 0; i < NP; ++i) {
+            const int fo = f2ord(walking ? obox[i] : 0.0f), fv = f2ord(walking ? vbox[i] : 0.0f);
+            const int olo = __reduce_min_sync(FULL, walking ? fo : INT_MAX);
+            const int ohi = __reduce_max_sync(FULL, walking ? fo : INT_MIN);
+            const int vlo = __reduce_min_sync(FULL, walking ? fv : INT_MAX);
+            const int vhi = __reduce_max_sync(FULL, walking ? fv : INT_MIN);
+            if (ws.lane == 0) ws.bundle[i] = make_float4(ord2f(olo), ord2f(ohi), ord2f(vlo), ord2f(vhi));
+        }
+        __syncwarp();
+    }
+#endif
 
     double lt = DBL_MAX;
     int lret = 0, lid = -1, lwin = -1;
