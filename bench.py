@@ -60,6 +60,9 @@ WORKLOADS = {
                      "(hplane, hcylinder, hdisk, hfacet; 6 lights, shadow rays), loaded by the reference's "
                      "scene_read_yaml over yaml_lite", "yaml", 10, "tests/scenes/config5_mixed10d.yaml", 0),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (both k_trace launches of generation 0), from the
+# ncu --set full capture of the same frame (profiles/r01_ncu_k_trace_bundle_*): 1.1 + 68.7 MB and 238.8 + 86.0 MB
+NCU_TRAFFIC_GB = {"config2": 0.3945}
 FRAMES_PER_GPU = 4
 TILES_PER_FRAME = 1
 IN_FLIGHT = int(os.environ.get("NDT_IN_FLIGHT", "2"))           # frames in flight per GPU: one ndt_b200 context (own CUDA stream) and one host thread each
@@ -381,10 +384,13 @@ def run_ours(args, rank, world, local_rank):
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak_nf / 1e3, "unit": "TFLOP/s",
             "frac": achieved / (peak_nf / 1e3) if peak_nf else None,
-            "traffic": None,
-            "kernel": "k_trace<8,0> + k_trace<8,1> (nearest-hit and shadow queries; 85 % of a frame, launch list in "
-                      "profiles/) timed with CUDA events as ONE whole frame alone on the GPU, k_shade/k_resolve/"
-                      "k_finish included in the denominator",
+            "traffic": NCU_TRAFFIC_GB.get(args.workload),
+            "traffic_unit": "GB of DRAM reads+writes of the two k_trace launches of generation 0 (ncu --set full, "
+                            "profiles/r01_ncu_k_trace_bundle_details.txt): the scene is L2-resident, the traffic is "
+                            "ray queues and hit records; against ~25 GFLOP of algorithmic work in the same launches",
+            "kernel": "k_trace<NP,0> + k_trace<NP,1> (nearest-hit and shadow queries; 54 % of a frame's kernel time on "
+                      "config 2, k_shade 39 %, k_finish 7 %: launch list in profiles/) timed with CUDA events as ONE "
+                      "whole frame alone on the GPU, k_shade/k_resolve/k_finish included in the denominator",
             "frame_ms_alone": solo_ms,
             "algorithmic_flops_per_frame": flops_frame,
             "peak_source": "measured live by ndt_b200_fp64_peak: non-fused DMUL+DADD chains on all SMs "

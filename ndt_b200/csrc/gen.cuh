@@ -26,14 +26,15 @@ using namespace ndt;
  * neighbour's, so 8-byte accesses touched 32 sectors per instruction and the load/store queue was the
  * stall of k_shade (ncu: lg 14 %) */
 template <int NP>
-__device__ __forceinline__ void ray_store(RayIn<NP> *out, const double *o, const double *v, double frac, int depth)
+__device__ __forceinline__ void ray_store(RayIn<NP> *out, const double *o, const double *v, double frac, int depth,
+                                          int aux = 0)
 {
     double2 *d = reinterpret_cast<double2 *>(out);
     NDT_UNROLL
     for (int i = 0; i < NP; i += 2) d[i / 2] = make_double2(o[i], o[i + 1]);
     NDT_UNROLL
     for (int i = 0; i < NP; i += 2) d[NP / 2 + i / 2] = make_double2(v[i], v[i + 1]);
-    d[NP] = make_double2(frac, __hiloint2double(0, depth));     /* frac | depth, pad */
+    d[NP] = make_double2(frac, __hiloint2double(aux, depth));   /* frac | depth, aux (shadow queries: where the answer goes) */
 }
 template <int NP>
 __device__ __forceinline__ void ray_load(const RayIn<NP> *in, double *o, double *v, double &frac, int &depth)
@@ -46,6 +47,11 @@ __device__ __forceinline__ void ray_load(const RayIn<NP> *in, double *o, double 
     const double2 t = d[NP];
     frac = t.x;
     depth = __double2loint(t.y);
+}
+template <int NP>
+__device__ __forceinline__ int ray_aux(const RayIn<NP> *in)
+{
+    return __double2hiint(reinterpret_cast<const double2 *>(in)[NP].y);
 }
 __device__ __forceinline__ void rec_load(RayRec &r, const RayRec *src)
 {
@@ -317,8 +323,10 @@ struct WaveArgs {
     HitRec *hits;            /* [cap], by slot */
     void *srays;             /* shadow queries RayIn<NP>[scap]: frac = dist_limit, depth = 1 + light index for the
                                 any-hit query of a DIRECTIONAL light, else 0 */
-    HitRec *shits;           /* [scap] */
-    int *sslot;              /* [count * n_lights]: shadow slot of (ray, light) or -1 */
+    HitRec *shits;           /* [count * n_lights]: the answer to the shadow query of (ray, light) at [ray * n_lights + light];
+                                the query carries that index (ray_aux), so k_shade<B> reads its answers without an
+                                indirection and can start all of them at once (entries without a query are never read) */
+    int *sslot;              /* unused */
     int scap;
     int *ctr;                /* [0] tail [1] next (radiance) [2] pool overflow [3] kd overflow / staging fault
                                 [4] shadow tail [5] next (shadow) */
@@ -378,15 +386,28 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
     }
     int *next = a.ctr + (MODE ? 5 : 1);
 
+#ifdef NDT_PREFETCH_WORK
+    /* the work counter is fetched one batch ahead: the atomic's round trip (ncu: 5 % of the samples, all
+     * long_scoreboard) overlaps the batch being traced; a warp overshoots the counter by one batch at the end */
+    int ahead = 0;
+    if (lane == 0) ahead = atomicAdd(next, 32);
+#endif
     while (true) {
         int base = 0;
+#ifdef NDT_PREFETCH_WORK
+        base = __shfl_sync(FULL, ahead, 0);
+        if (base >= count) break;
+        if (lane == 0) ahead = atomicAdd(next, 32);
+#else
         if (lane == 0) base = atomicAdd(next, 32);
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
+#endif
         const int r = base + lane;
         double o[NP], v[NP], limit = -1.0;
         bool want;
         int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
+        int dest = 0;                /* MODE 1: index of the answer in shits[] */
         if (MODE == 0) {
             double frac; int depth, tx, ty;
             want = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
@@ -396,12 +417,13 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
                 int code;
                 ray_load<NP>((const RayIn<NP> *)a.srays + r, o, v, limit, code);
                 dir_light = code - 1;
+                dest = ray_aux<NP>((const RayIn<NP> *)a.srays + r);
             }
         }
         Hit T;
         trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
         if (ws.fault) break;     /* warp-uniform (warp.cuh) */
-        if (want) hit_store(MODE == 0 ? a.hits + (a.start + r) : a.shits + r, T.t, T.id, T.win, T.found);
+        if (want) hit_store(MODE == 0 ? a.hits + (a.start + r) : a.shits + dest, T.t, T.id, T.win, T.found);
     }
     if (kd_overflow) atomicMax(a.ctr + 3, 1);
     if (ws.fault) atomicMax(a.ctr + 3, 2);
@@ -426,6 +448,18 @@ const Scene sc, const WaveArgs a)
     Hit T0;
     T0.t = -1; T0.id = -1; T0.win = -1; T0.found = 0;
     if (r < a.count) hit_load(a.hits + (a.start + r), T0.t, T0.id, T0.win, T0.found);
+    /* phase B: the answers of the first lights as well (k_shade is latency bound: ncu long_scoreboard 41 %,
+     * the slot -> answer chain of every light was on the critical path) */
+    constexpr int PF = 3;
+    Hit P[PF];
+    const int nl = sc.n_lights;
+    if (PHASE == 1) {
+        NDT_UNROLL
+        for (int k = 0; k < PF; ++k) {
+            P[k].t = -1; P[k].id = -1; P[k].win = -1; P[k].found = 0;
+            if (r < a.count && k < nl) hit_load(a.shits + ((size_t)r * nl + k), P[k].t, P[k].id, P[k].win, P[k].found);
+        }
+    }
     const bool active = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
     Tally<false> none;
     Shade<NP> S;
@@ -439,7 +473,6 @@ const Scene sc, const WaveArgs a)
         shade_setup<NP, false>(sc, S, -1, o, v, nsh, none);
         shade_after<NP, false>(sc, S, -1, T0, o, v, rec, p_hit, p_id, p_dist, none);
     }
-    const int nl = sc.n_lights;
     if (__ballot_sync(FULL, active && S.shaded)) {
         for (int it = 0; it < nl; ++it) {
             const bool want = active && shade_setup<NP, false>(sc, S, it, o, v, nsh, none);
@@ -459,19 +492,19 @@ const Scene sc, const WaveArgs a)
                         if (slot < a.scap) {
                             /* depth = light index + 1 for the any-hit query of a DIRECTIONAL light */
                             ray_store<NP>((RayIn<NP> *)a.srays + slot, S.ro, S.rv, S.limit,
-                                          S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0);
+                                          S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0, r * nl + it);
                         } else {
-                            atomicExch(a.ctr + 2, 1);
-                            slot = -1;
+                            atomicExch(a.ctr + 2, 1);   /* the render fails with NDT_B200_E_OVERFLOW */
                         }
                     }
-                    a.sslot[(size_t)r * nl + it] = slot;
                 }
             } else if (want) {
-                const int slot = a.sslot[(size_t)r * nl + it];
                 Hit T;
-                T.t = -1; T.id = -1; T.win = -1; T.found = 0;
-                if (slot >= 0) hit_load(a.shits + slot, T.t, T.id, T.win, T.found);
+                if (it < PF) {
+                    T = it == 0 ? P[0] : (it == 1 ? P[1] : P[2]);
+                } else {
+                    hit_load(a.shits + ((size_t)r * nl + it), T.t, T.id, T.win, T.found);
+                }
                 shade_after<NP, false>(sc, S, it, T, o, v, rec, p_hit, p_id, p_dist, none);
             }
         }

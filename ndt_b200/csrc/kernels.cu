@@ -487,8 +487,10 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
             const size_t scap = (size_t)count * (size_t)(n_sh > 0 ? n_sh : 1);
             if (scap > 0x7ffffff0u) return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow queue too large; render a smaller tile");
             if ((r = grow(c, (void **)&c->d_srays, &c->srays_bytes, scap * rayin_bytes(np)))) return r;
-            if ((r = grow(c, (void **)&c->d_shits, &c->shits_cap, scap * sizeof(HitRec)))) return r;
-            if ((r = grow(c, (void **)&c->d_sslot, &c->sslot_cap, (size_t)count * (size_t)(h.n_lights > 0 ? h.n_lights : 1) * sizeof(int)))) return r;
+            /* answers are indexed [ray * n_lights + light] (gen.cuh) */
+            const size_t nans = (size_t)count * (size_t)(h.n_lights > 0 ? h.n_lights : 1);
+            if (nans > 0x7ffffff0u) return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow answers too large; render a smaller tile");
+            if ((r = grow(c, (void **)&c->d_shits, &c->shits_cap, nans * sizeof(HitRec)))) return r;
             a.srays = c->d_srays; a.shits = c->d_shits; a.sslot = c->d_sslot; a.scap = (int)scap;
             a.gen = ngen; a.start = start; a.count = count;
             if (ngen > 0) {      /* work counters and the shadow tail start from zero */
