@@ -388,8 +388,8 @@ def run_ours(args, rank, world, local_rank):
             "traffic_unit": "GB of DRAM reads+writes of the two k_trace launches of generation 0 (ncu --set full, "
                             "profiles/r01_ncu_k_trace_bundle_details.txt): the scene is L2-resident, the traffic is "
                             "ray queues and hit records; against ~25 GFLOP of algorithmic work in the same launches",
-            "kernel": "k_trace<NP,0> + k_trace<NP,1> (nearest-hit and shadow queries; 54 % of a frame's kernel time on "
-                      "config 2, k_shade 39 %, k_finish 7 %: launch list in profiles/) timed with CUDA events as ONE "
+            "kernel": "k_trace<NP,0> + k_trace<NP,1> (nearest-hit and shadow queries; 52 % of a frame's kernel time on "
+                      "config 2, k_shade 38 %, k_finish 10 %: launch list in profiles/) timed with CUDA events as ONE "
                       "whole frame alone on the GPU, k_shade/k_resolve/k_finish included in the denominator",
             "frame_ms_alone": solo_ms,
             "algorithmic_flops_per_frame": flops_frame,
