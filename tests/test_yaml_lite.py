@@ -263,6 +263,24 @@ def test_reference_emitter_over_yaml_lite_writes_what_libyaml_writes(ref, tmp_pa
 
 
 @needs_ref
+def test_reference_buffer_writer_grows_its_buffer(ref, tmp_path):
+    """BASELINE config 2 as YAML is larger than scene_write_yaml_buffer's first 1 MiB buffer (scene.c:1062): the
+    emitter must report the overflow the way libyaml's string writer does (size_written == size) so that the
+    reference doubles the buffer and tries again (scene.c:1066-1085).  Both writers, one text, libyaml's events."""
+    ref.open_scene("hypercube")
+    f1 = str(tmp_path / "a.yaml"); f2 = str(tmp_path / "b.yaml")
+    ref.write_yaml(8, 0, 300, f1, None)
+    ref.write_yaml(8, 0, 300, f2, None, to_buffer=True)
+    text = open(f1, "rb").read()
+    assert len(text) > (1 << 20)
+    assert text == open(f2, "rb").read()
+    err, listing = libyaml_events(text)
+    rc, mine = lite_events(text)
+    assert err == 0 and rc == 0 and mine == listing
+    assert listing.count("=VAL 10p type") >= 6561
+
+
+@needs_ref
 def test_yaml_scene_reload_is_a_fixed_point(ref, tmp_path):
     """C scene -> YAML -> scene -> YAML -> scene: the second and third generation are identical text and
     identical flat scenes.  (The first reload legitimately differs from the C scene: the ambient light
