@@ -82,6 +82,21 @@ def test_parser_events_equal_libyaml_on_scene_files(name):
     assert mine.count("+DOC") == (3 if name.startswith("hand") else 1)
 
 
+@pytest.mark.parametrize("name", ["config5_mixed10d.yaml", "handwritten4d.yaml"])
+def test_parser_reads_the_layouts_of_another_emitter(name):
+    """the same scenes re-written by PyYAML's own (pure Python) emitter in five layouts -- all block, all flow,
+    4-space indent at width 60, explicit document markers at width 1000: same events as libyaml reads"""
+    import yaml
+    docs = list(yaml.safe_load_all(open(os.path.join(SCENES, name))))
+    for kw in (dict(default_flow_style=None), dict(default_flow_style=False), dict(default_flow_style=True),
+               dict(default_flow_style=None, indent=4, width=60),
+               dict(default_flow_style=None, explicit_start=True, explicit_end=True, width=1000)):
+        text = yaml.safe_dump_all(docs, **kw).encode()
+        rc, mine = lite_events(text)
+        err, theirs = libyaml_events(text)
+        assert rc == 0 and err == 0 and mine == theirs, kw
+
+
 @pytest.mark.parametrize("i", range(len(HAND)))
 def test_parser_events_equal_libyaml_handwritten(i):
     rc, mine = lite_events(HAND[i])
