@@ -259,7 +259,8 @@ def run_ours(args, rank, world, local_rank):
         if errs:
             raise errs[0]
 
-    def device_step(_unused, upload):
+    def device_step(_unused, upload, frames=None):
+        frames = frames_dev if frames is None else frames
         step_id = serial[0]                               # queue keys must never repeat within a job
         serial[0] += 1
         if upload:
@@ -279,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
                     k = len(mine)
                     mine.append(idx)
                 f, y0, th = items[idx]
-                dst = frames_dev[f, y0:y0 + th] if rank == 0 else stage[k, :th]
+                dst = frames[f, y0:y0 + th] if rank == 0 else stage[k, :th]
                 c.launch_tile(0, y0, W, th, d_u8=dst.data_ptr())
                 st = c.sync()
                 with lock:
@@ -288,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
                     totals["launches"] += st.launches
         run_workers(work)
         if world > 1:
-            multi.gather_tiles(dist, rank, world, items, mine, stage, frames_dev, band)
+            multi.gather_tiles(dist, rank, world, items, mine, stage, frames, band)
         return mine
 
     def timed(fn, k, w):
@@ -368,11 +369,29 @@ def run_ours(args, rank, world, local_rank):
             run_workers(work)
         d2h = n_frames * H * W * 4
     else:
+        # rank 0 reads every step's frames back to pinned host memory.  The read of step i runs on a copy stream
+        # while step i+1 renders into the other of two frame buffers (at N = 8 the 265 MB per step over rank 0's
+        # one PCIe link would otherwise serialise behind the render); every copy completes inside the timed region
+        # (timed() ends with barrier + device synchronize).
+        dev_bufs = [frames_dev, torch.zeros_like(frames_dev)] if rank == 0 else [None, None]
+        host_bufs = [frames_host, torch.zeros_like(frames_host).pin_memory()] if rank == 0 else [None, None]
+        copy_stream = torch.cuda.Stream(device=dev) if rank == 0 else None
+        copy_done = [None, None]
+
         def e2e_step(i):
-            device_step(i, True)
+            b = i & 1
+            if rank == 0 and copy_done[b] is not None:
+                copy_done[b].synchronize()                  # the read-back of two steps ago still owns this buffer
+            device_step(i, True, dev_bufs[b])
             if rank == 0:
-                frames_host.copy_(frames_dev, non_blocking=True)
-                torch.cuda.synchronize()
+                ready = torch.cuda.Event()
+                ready.record()                              # after the gather on the current stream
+                copy_stream.wait_event(ready)
+                with torch.cuda.stream(copy_stream):
+                    host_bufs[b].copy_(dev_bufs[b], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                copy_done[b] = done
         d2h = n_frames * H * W * 4
     edt, erays, _, _ = timed(e2e_step, args.steps, max(1, args.warmup // 2))
     e2e_value = erays / edt / 1e6
@@ -425,7 +444,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_s": frames_total / edt,
-                    "path": "ndt_b200_upload + ndt_b200_render_tile (host buffers)" if world == 1 else
+                    "path": ("ndt_b200_upload + ndt_b200_render_tile (host buffers)" if world == 1 else
+                             "ndt_b200_upload + launch_tile + NCCL gather to rank 0 + read-back to rank 0's pinned host "
+                             "memory on a copy stream, double buffered") if world == 1 else
                             "upload + device render + NCCL gather + rank-0 D2H"},
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -147,6 +147,22 @@ __global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out, BoxRec
             if (!(qa >= EPS)) r.par_mask |= 1u << l;
         }
     }
+    else if (bs[NP] > 0 && sc.any_boxed) {
+        /* any other primitive with a bounding sphere: the sphere's own box.  A ray that misses it misses the
+         * sphere, so the reference's pre-test (bounding.c:52-84) rejects the object before its intersect() is
+         * called -- for every kind of query, hence no par_mask.  The margin (0.03) dwarfs what fp64 rounding can
+         * move desc by at |coordinates| < 2e4 (ndt_b200_upload).  What it buys: the fp32 slab test and the bundle
+         * cull run ahead of the fp64 sphere test for every record of a large leaf (BASELINE config 3: the kd
+         * tree cannot separate 10 000 overlapping 6-D objects, a leaf holds them all). */
+        const double rr = bs[NP];
+        for (int k = 0; k < sc.n; ++k) {
+            const double mg = 0.03 + 1e-9 * (fabs(bs[k]) + rr);
+            bx.lo[k] = __double2float_rd(bs[k] - rr - mg);
+            bx.hi[k] = __double2float_ru(bs[k] + rr + mg);
+        }
+        r.boxed = 1;
+        r.par_mask = 0;
+    }
     out[i] = r;
     box_out[i] = bx;
 }

@@ -296,8 +296,11 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     s.any_boxed = 0;
     {   /* k_pack_leaf gives orthotopes with a bounding sphere a box (warp.cuh: box_hit) */
         const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
+        /* ... and, in boxed scenes, every other primitive the box of its bounding sphere.  Scenes without
+         * orthotopes only pay for the second record stream when their leaves are large enough for the culls to
+         * matter */
         for (int i = 0; i < h->n_items && !s.any_boxed; ++i)
-            if (ho[i].type == NDT_T_ORTHOTOPE && ho[i].bs_radius > 0) s.any_boxed = 1;
+            if (ho[i].bs_radius > 0 && (ho[i].type == NDT_T_ORTHOTOPE || h->max_leaf >= 48)) s.any_boxed = 1;
         /* the slab test runs in fp32 with a fixed margin (warp.cuh: box_hit): only for scenes whose
          * coordinates keep its rounding error far below that margin */
         if (s.any_boxed) {
