@@ -446,8 +446,7 @@ def run_ours(args, rank, world, local_rank):
                     "frames_per_s": frames_total / edt,
                     "path": ("ndt_b200_upload + ndt_b200_render_tile (host buffers)" if world == 1 else
                              "ndt_b200_upload + launch_tile + NCCL gather to rank 0 + read-back to rank 0's pinned host "
-                             "memory on a copy stream, double buffered") if world == 1 else
-                            "upload + device render + NCCL gather + rank-0 D2H"},
+                             "memory on a copy stream, double buffered")},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
