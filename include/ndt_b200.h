@@ -206,6 +206,11 @@ int ndt_b200_trace_rays(ndt_b200_ctx *ctx, int n_rays, const double *origins, co
  * denominators of bench.py */
 int ndt_b200_fp64_peak(ndt_b200_ctx *ctx, int fused, double *gflops);
 
+/* the sample loop of get_pixel_color (ndt.c:488-568) for n traced colours rgba_in[n][4]: the averaged colour
+ * the loop converges to (rgba_out[n][4]) and the number of identical samples it takes (samples[n]).  k_finish
+ * runs exactly this per pixel; exposed as the probe of the known-answer test of its division sequence. */
+int ndt_b200_replay_samples(ndt_b200_ctx *ctx, int n, const double *rgba_in, double *rgba_out, int32_t *samples);
+
 const char *ndt_b200_last_error(void);
 const char *ndt_b200_version(void);
 

@@ -109,6 +109,7 @@ def lib():
     L.ndt_b200_host_free.restype = None
     L.ndt_b200_trace_rays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     L.ndt_b200_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.ndt_b200_replay_samples.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ndt_b200_render_image.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_HostApi), C.c_char_p, C.c_char_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -314,6 +315,13 @@ class Context:
         _check(lib().ndt_b200_trace_rays(self._h, n, o.ctypes.data, v.ctypes.data, _p(lim), found.ctypes.data,
                                          oid.ctypes.data, t.ctypes.data, hit.ctypes.data, nrm.ctypes.data))
         return found, oid, t, hit, nrm
+
+    def replay_samples(self, rgba):
+        """ndt_b200_replay_samples: (averaged colours [n,4], samples taken [n]) for traced colours [n,4]"""
+        a = np.ascontiguousarray(rgba, np.float64).reshape(-1, 4)
+        out = np.zeros_like(a); ns = np.zeros(len(a), np.int32)
+        _check(lib().ndt_b200_replay_samples(self._h, len(a), a.ctypes.data, out.ctypes.data, ns.ctypes.data))
+        return out, ns
 
     def fp64_peak(self, fused):
         g = C.c_double(0)

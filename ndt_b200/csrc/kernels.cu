@@ -735,6 +735,39 @@ extern "C" void *ndt_b200_host_alloc(size_t bytes)
 }
 extern "C" void ndt_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+__global__ void k_replay_probe(int n, const double *in, double *out, int32_t *ns)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double l[4] = { in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3] };
+    double o[4];
+    ns[i] = replay_samples(l, o);
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = o[k];
+}
+
+extern "C" int ndt_b200_replay_samples(ndt_b200_ctx *c, int n, const double *rgba_in, double *rgba_out, int32_t *samples)
+{
+    if (!c || !rgba_in || !rgba_out || !samples || n < 0) return ndt_set_error(NDT_B200_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    double *d_in = NULL, *d_out = NULL;
+    int32_t *d_ns = NULL;
+    cudaError_t e = cudaMalloc(&d_in, (size_t)n * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ns, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, rgba_in, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        k_replay_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(n, d_in, d_out, d_ns);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgba_out, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(samples, d_ns, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ns);
+    if (e != cudaSuccess) return ndt_set_error(NDT_B200_E_CUDA, "ndt_b200_replay_samples: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int ndt_b200_fp64_peak(ndt_b200_ctx *c, int fused, double *gflops)
 {
     if (!c || !gflops) return ndt_set_error(NDT_B200_E_ARG, "NULL argument");

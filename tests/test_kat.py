@@ -70,3 +70,40 @@ def test_cuda_answers_the_reference_kats(case):
     assert same_bits(nr[m], nrm[m])
     d = np.sqrt(((h[m] - o[m]) ** 2).sum(axis=1))
     assert np.allclose(t[m], d, rtol=1e-12)
+
+
+def _ref_replay(l):
+    """get_pixel_color's sample loop for samples=1 (ndt.c:488-568), literally: six divisions per re-sample"""
+    t = [0.0, 0.0, 0.0, 0.0]
+    ts, clr_diff, i = 0, 256.0, 0
+    while i < 1 or (i < 10000 and clr_diff > 1.0 / 256.0):
+        if i > 1:
+            d = [abs(t[k] / (i - 1) - (t[k] + l[k]) / i) for k in range(3)]
+            clr_diff = d[0] if d[0] > (d[1] if d[1] > d[2] else d[2]) else (d[1] if d[1] > d[2] else d[2])
+        for k in range(4):
+            t[k] += l[k]
+        ts += 1
+        i += 1
+    return [t[k] / ts for k in range(4)], ts
+
+
+@pytest.mark.gpu
+def test_sample_loop_replay_known_answers():
+    """k_finish replays the reference's identical re-samples with three divisions per sample that share one
+    reciprocal (core.cuh: replay_samples, divn_shared).  Bit-exact against the literal loop in IEEE double
+    (Python floats) on colours across the range a frame can hold, incl. zeros, denormals, huge values, inf."""
+    import ndt_b200
+    rng = np.random.default_rng(7)
+    cols = [rng.uniform(0, 1.5, size=(1500, 4)), rng.uniform(0, 400, size=(300, 4)),
+            10.0 ** rng.uniform(-320, 300, size=(300, 4)), rng.uniform(-2, 2, size=(200, 4))]
+    special = [0.0, -0.0, 1.0, 0.5, 1.0 / 256, 1.0 / 512, 2.0 / 256, 5e-324, 1e-310, 1.7e308, np.inf, 255.0, 1e-4, 3.0]
+    cols.append(np.array([[a, b, c, 1.0] for a in special for b in (0.0, 0.3) for c in (0.0, 1.0 / 3)]))
+    cols = np.vstack(cols)
+    with ndt_b200.Context(0) as ctx:
+        out, ns = ctx.replay_samples(cols)
+    for k in range(len(cols)):
+        want, ts = _ref_replay([float(x) for x in cols[k]])
+        assert ns[k] == ts, (k, cols[k], ns[k], ts)
+        got = out[k]
+        for c in range(4):
+            assert (got[c] == want[c]) or (got[c] != got[c] and want[c] != want[c]), (k, c, cols[k], got[c], want[c])
