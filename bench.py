@@ -267,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
             for c in ctxs:
                 c.upload(flat)
         flush.fill_(step_id & 0xFF)                       # L2 flush between steps
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()         # not the whole device: a read-back of the previous step may still run
         mine = []
         pull = queue.pull(step_id, len(items))
 
