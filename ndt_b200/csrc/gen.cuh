@@ -402,23 +402,12 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
     }
     int *next = a.ctr + (MODE ? 5 : 1);
 
-#ifdef NDT_PREFETCH_WORK
-    /* the work counter is fetched one batch ahead: the atomic's round trip (ncu: 5 % of the samples, all
-     * long_scoreboard) overlaps the batch being traced; a warp overshoots the counter by one batch at the end */
-    int ahead = 0;
-    if (lane == 0) ahead = atomicAdd(next, 32);
-#endif
     while (true) {
+        /* (fetching the counter one batch ahead was measured slower: profiles/r01_experiments.md) */
         int base = 0;
-#ifdef NDT_PREFETCH_WORK
-        base = __shfl_sync(FULL, ahead, 0);
-        if (base >= count) break;
-        if (lane == 0) ahead = atomicAdd(next, 32);
-#else
         if (lane == 0) base = atomicAdd(next, 32);
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
-#endif
         const int r = base + lane;
         double o[NP], v[NP], limit = -1.0;
         bool want;

@@ -258,12 +258,12 @@ template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const
  * points; IEEE rounding is monotone, so tmin_lb <= every ray's computed tmin and tmax_ub >= every ray's
  * computed tmax: a record dropped here would have failed box_hit for every ray of the bundle (the per-ray
  * result is unchanged, bit for bit).  Axes on which the rays do not all run the same way (or some are
- * parallel and some not) give no constraint; if all are parallel (1/v = +-inf, box_hit's inf arithmetic)
- * the record is dropped when every origin lies outside the slab. */
+ * parallel and some not) give no constraint; if all are parallel (1/v = +-inf) and every origin lies on one
+ * side of the slab, tmin / tmax take the +-inf box_hit computes for each of them.  tests/test_bundle_math.py
+ * restates both functions in numpy fp32 and checks the implication on random bundles. */
 template <int NP> __device__ __forceinline__ bool bundle_hit(const float *lo, const float *hi, const float4 *bd)
 {
     float tmin = 0.0f, tmax = FLT_MAX;
-    bool outside = false;
     /* rolled: once per chunk and warp, not worth instruction-cache space (unrolled, the hit rate of the SM
      * instruction cache fell from 98 % to 80 %) */
     NDT_NO_UNROLL
@@ -279,10 +279,12 @@ template <int NP> __device__ __forceinline__ bool bundle_hit(const float *lo, co
             tmin = fmaxf(tmin, fminf(__fmul_rn(d, b.z), __fmul_rn(d, b.w)));
             tmax = fminf(tmax, fmaxf(__fmul_rn(a, b.z), __fmul_rn(a, b.w)));
         } else if (b.z == b.w && (b.z > FLT_MAX || b.z < -FLT_MAX)) {   /* all parallel to the slab */
-            if (b.x > h || b.y < l) outside = true;
+            /* box_hit's own values: (l-o) inf and (h-o) inf are both -inf behind the slab, both +inf before it */
+            if (b.x > h) tmax = -INFINITY;
+            if (b.y < l) tmin = INFINITY;
         }
     }
-    return !outside && tmin <= tmax * 1.000001f + 1e-30f;
+    return tmin <= tmax * 1.000001f + 1e-30f;
 }
 /* order-preserving float <-> int, for redux.sync (integer only) */
 __device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
