@@ -11,8 +11,8 @@
  * make the very same object_add_* / scene_alloc_light calls for a given file.
  *
  * What it is: an event producer for the YAML subset scenes are written in
- * (block and flow mappings / sequences, plain and quoted scalars, comments,
- * multi-document streams) and an event consumer that writes the text libyaml
+ * (block and flow mappings / sequences, plain scalars incl. multi-line ones, quoted
+ * scalars, comments, multi-document streams) and an event consumer that writes the text libyaml
  * 0.2.5 writes for the same events (block/flow layout, 80-column folding of
  * flow sequences, scalar style selection and quoting).  Both are pinned against
  * libyaml 0.2.5 itself (PyYAML's CParser / CEmitter) in tests/test_yaml_lite.py.

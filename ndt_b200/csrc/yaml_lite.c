@@ -148,6 +148,7 @@ struct ylite_parser_impl {
     unsigned char *sc;           /* scalar scratch */
     size_t sc_n, sc_cap;
     size_t sc_floor;             /* scratch bytes produced by escapes: not trimmed when a line folds */
+    size_t plain_indent;         /* block context: a plain scalar continues on lines indented at least this far */
 };
 typedef struct ylite_parser_impl P;
 
@@ -414,17 +415,42 @@ static int scan_plain(P *p, int flow)
     if (is_flowind(c) || c == '#')
         return p_fail(p, YAML_SCANNER_ERROR, "found character that cannot start any token");
     for (;;) {
+        for (;;) {
+            c = pk(p, 0);
+            if (at_eof(p) || is_brk(c)) break;
+            if (c == ':' && is_blankz(pk(p, 1))) break;
+            if (flow && c == ':' && is_flowind(pk(p, 1)))
+                return p_fail(p, YAML_SCANNER_ERROR, "found unexpected ':'");
+            if (flow && is_flowind(c)) break;
+            if (c == '#' && p->sc_n && is_blank(p->sc[p->sc_n - 1])) break;
+            if (!sc_put(p, c)) return 0;
+            p_adv(p);
+        }
+        while (p->sc_n && is_blank(p->sc[p->sc_n - 1])) p->sc_n--;
+        if (!is_brk(pk(p, 0)) || at_eof(p)) break;
+        /* a plain scalar continues on the next non-empty line when that line is content indented far enough
+         * (block context) and does not start with something that ends a plain scalar: one break folds into a
+         * space, k breaks into k-1 line feeds (libyaml: yaml_parser_scan_plain_scalar) */
+        const size_t s_pos = p->pos, s_line = p->line, s_col = p->col;
+        int breaks = 0, tab_indent = 0;
+        for (;;) {
+            if (is_brk(pk(p, 0))) { p_brk(p); breaks++; continue; }
+            if (pk(p, 0) == ' ') { p_adv(p); continue; }
+            if (pk(p, 0) == '\t') { tab_indent = 1; p_adv(p); continue; }
+            break;
+        }
         c = pk(p, 0);
-        if (at_eof(p) || is_brk(c)) break;
-        if (c == ':' && is_blankz(pk(p, 1))) break;
-        if (flow && c == ':' && is_flowind(pk(p, 1)))
-            return p_fail(p, YAML_SCANNER_ERROR, "found unexpected ':'");
-        if (flow && is_flowind(c)) break;
-        if (c == '#' && p->sc_n && is_blank(p->sc[p->sc_n - 1])) break;
-        if (!sc_put(p, c)) return 0;
-        p_adv(p);
+        int cont = !at_eof(p) && !at_marker(p) && c != '#';
+        if (cont && !flow && p->col < p->plain_indent) cont = 0;
+        if (cont && flow && (c == ',' || c == ']' || c == '}' ||
+                             (c == ':' && (is_blankz(pk(p, 1)) || is_flowind(pk(p, 1)))))) cont = 0;
+        if (cont && !flow && tab_indent && p->col < p->plain_indent) cont = 0;
+        if (!cont) { p->pos = s_pos; p->line = s_line; p->col = s_col; break; }
+        if (c == ':' && is_blankz(pk(p, 1)))
+            return p_fail(p, YAML_SCANNER_ERROR, "mapping values are not allowed in this context");
+        if (breaks == 1) { if (!sc_put(p, ' ')) return 0; }
+        else for (int i = 1; i < breaks; ++i) if (!sc_put(p, '\n')) return 0;
     }
-    while (p->sc_n && is_blank(p->sc[p->sc_n - 1])) p->sc_n--;
     return 1;
 }
 
@@ -465,9 +491,13 @@ static int parse_flow_seq(P *p)
         if (!skip_flow_space(p)) return 0;
         if (pk(p, 0) == ']') { p_adv(p); break; }
         size_t at = p->nev;
+        const size_t key_line = p->line;
         int q = (pk(p, 0) == '\'' || pk(p, 0) == '"');
         if (!parse_flow_node(p)) return 0;
+        const int one_line = p->line == key_line;
         if (!skip_flow_space(p)) return 0;
+        if (flow_colon(p, q) && p->nev == at + 1 && !one_line)
+            return p_fail(p, YAML_SCANNER_ERROR, "mapping values are not allowed in this context (a simple key may not span lines)");
         if (flow_colon(p, q) && p->nev == at + 1) {
             /* single-pair mapping inside a flow sequence: [a: b] */
             if (!p_push(p, YAML_NO_EVENT)) return 0;
@@ -504,7 +534,18 @@ static int parse_flow_map(P *p)
         int q = (pk(p, 0) == '\'' || pk(p, 0) == '"');
         if (pk(p, 0) == ':' && (is_blankz(pk(p, 1)) || is_flowind(pk(p, 1)))) {
             if (!p_empty(p)) return 0;       /* {: v} */
-        } else if (!parse_flow_node(p)) return 0;
+        } else {
+            const size_t key_line = p->line;
+            if (!parse_flow_node(p)) return 0;
+            if (p->line != key_line && p->ev[p->nev - 1].type == YAML_SCALAR_EVENT) {
+                /* a key that spans lines is only legal when no ':' follows it */
+                const size_t s_pos = p->pos, s_line = p->line, s_col = p->col;
+                if (!skip_flow_space(p)) return 0;
+                if (flow_colon(p, q))
+                    return p_fail(p, YAML_SCANNER_ERROR, "mapping values are not allowed in this context (a simple key may not span lines)");
+                p->pos = s_pos; p->line = s_line; p->col = s_col;
+            }
+        }
         if (!skip_flow_space(p)) return 0;
         if (flow_colon(p, q)) {
             p_adv(p);
@@ -526,21 +567,6 @@ static int parse_flow_node(P *p)
     if (c == '[') return parse_flow_seq(p);
     if (c == '{') return parse_flow_map(p);
     if (!scan_scalar(p, 1, &style)) return 0;
-    if (style == YAML_PLAIN_SCALAR_STYLE && at_line_end(p)) {
-        /* a plain scalar may not continue on the next line here (multi-line plain scalars: out of scope) */
-        size_t n = p->sc_n;
-        unsigned char *keep = dup_n(p->sc, n);
-        if (!keep) return p_fail(p, YAML_MEMORY_ERROR, "out of memory");
-        int ok = skip_flow_space(p);
-        if (ok) {
-            int d = pk(p, 0);
-            if (!(d == ',' || d == ']' || d == '}' || (d == ':' && (is_blankz(pk(p, 1)) || is_flowind(pk(p, 1))))))
-                ok = p_fail(p, YAML_SCANNER_ERROR, "multi-line plain scalars are not supported");
-        }
-        if (ok) ok = p_scalar(p, keep, n, YAML_PLAIN_SCALAR_STYLE);
-        free(keep);
-        return ok;
-    }
     return p_scalar(p, p->sc, p->sc_n, (yaml_scalar_style_t)style);
 }
 
@@ -562,6 +588,7 @@ static int expect_line_end(P *p)
 /* value of a block mapping key at indent n; positioned just after ':' */
 static int parse_map_value(P *p, size_t n)
 {
+    p->plain_indent = n + 1;
     skip_line_tail(p);
     if (at_line_end(p)) {
         if (!skip_to_content(p)) return 0;
@@ -595,9 +622,11 @@ static int parse_block_map(P *p, size_t n, int style)
         if (p->col > n) return p_fail(p, YAML_PARSER_ERROR, "did not find expected key (bad indentation of a mapping entry)");
         if (pk(p, 0) == '[' || pk(p, 0) == '{')
             return p_fail(p, YAML_PARSER_ERROR, "flow collections as mapping keys are not supported");
+        const size_t key_line = p->line;
+        p->plain_indent = n + 1;
         if (!scan_scalar(p, 0, &style)) return 0;
         while (is_blank(pk(p, 0))) p_adv(p);
-        if (!(pk(p, 0) == ':' && is_blankz(pk(p, 1))))
+        if (!(pk(p, 0) == ':' && is_blankz(pk(p, 1))) || p->line != key_line)
             return p_fail(p, YAML_SCANNER_ERROR, "could not find expected ':'");
     }
     return p_push(p, YAML_MAPPING_END_EVENT) != NULL;
@@ -611,6 +640,7 @@ static int parse_block_seq(P *p, size_t n, int indentless)
     e->data.sequence_start.implicit = 1;
     e->data.sequence_start.style = YAML_BLOCK_SEQUENCE_STYLE;
     for (;;) {
+        p->plain_indent = n + 1;
         p_adv(p);                                   /* '-' */
         skip_line_tail(p);
         if (at_line_end(p)) {
@@ -679,6 +709,7 @@ static void parse_stream(P *p)
         e->data.document_start.implicit = !explicit_start;
         first = 0;
         int have_node = 0;
+        p->plain_indent = 0;
         if (explicit_start) {
             p->pos += 3; p->col += 3;
             skip_line_tail(p);

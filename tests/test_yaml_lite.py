@@ -45,6 +45,8 @@ HAND = [
     b"---\na: 1\n...\n...\n---\nb: 2\n",
     b"a: {}\nb: []\nc: [[], {}]\n",
     b"sizes:\n- 5.0\n-   6\nflags: [ 0 ]\n",
+    b"- a\n b\n",
+    b"name: a long name\n  that continues\n\n  after a blank line   # comment\nnext: [one\n  two, three]\n--- top level\nplain\n",
 ]
 BAD = [
     b"a: b: c\n",
@@ -56,7 +58,6 @@ BAD = [
     b"a: [1, 2\nb: 3\n",
     b"a: 'open\n",
     b"a: 1\n  b: 2\n",
-    b"- a\n b\n",
     b"a:\n\t- 1\n",
     b"...\na: 1\n",
     b"a: 1\n...\nb: 2\n",
@@ -207,7 +208,7 @@ def test_emitter_folds_long_vectors_like_libyaml():
 def test_parser_events_equal_libyaml_on_random_documents():
     """libyaml writes random event streams (three widths); both parsers read them back.  Complex keys
     ("? ") are out of the subset: the generator keeps keys simple, and whatever yaml_lite still refuses
-    must be refused, not misread."""
+    must be refused, not misread (multi-line plain scalars, which libyaml writes at width 40, are read)."""
     rng = random.Random(77)
     refused = unreadable = 0
     for t in range(800):
@@ -220,10 +221,10 @@ def test_parser_events_equal_libyaml_on_random_documents():
         rc, mine = lite_events(text)
         if rc:
             refused += 1
-            assert rc in (3, 4)     # multi-line plain scalars, complex keys: an error, not a misreading
+            assert rc in (3, 4)     # complex keys: an error, not a misreading
             continue
         assert mine == theirs, f"document {t}:\n{text.decode()}"
-    assert refused < 80 and unreadable < 80, (refused, unreadable)
+    assert refused < 40 and unreadable < 80, (refused, unreadable)
 
 
 def test_roundtrip_through_both_directions():
