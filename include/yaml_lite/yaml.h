@@ -11,14 +11,14 @@
  * make the very same object_add_* / scene_alloc_light calls for a given file.
  *
  * What it is: an event producer for the YAML subset scenes are written in
- * (block and flow mappings / sequences, plain scalars incl. multi-line ones, quoted
- * scalars, comments, multi-document streams) and an event consumer that writes the text libyaml
+ * (block and flow mappings / sequences, complex "? " keys, plain scalars incl.
+ * multi-line ones, quoted scalars, comments, multi-document streams) and an event consumer that writes the text libyaml
  * 0.2.5 writes for the same events (block/flow layout, 80-column folding of
  * flow sequences, scalar style selection and quoting).  Both are pinned against
  * libyaml 0.2.5 itself (PyYAML's CParser / CEmitter) in tests/test_yaml_lite.py.
- * What it is not: anchors, aliases, tags, directives, block scalars and
- * complex keys are refused with a parser error (YAML_SCANNER_ERROR), never
- * guessed at.
+ * What it is not: anchors, aliases, tags, directives, block scalars and flow
+ * collections used as simple keys ("[a]: b") are refused with a parser error,
+ * never guessed at.
  *
  * Link names carry a ylite_ prefix (macros below) so the library can share a
  * process with a real libyaml.

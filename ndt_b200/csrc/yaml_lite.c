@@ -408,7 +408,7 @@ static int scan_plain(P *p, int flow)
     if (c == '&' || c == '*' || c == '!' || c == '|' || c == '>' || c == '%' || c == '@' || c == '`')
         return p_fail(p, YAML_SCANNER_ERROR, "anchors, aliases, tags, block scalars and reserved indicators are not supported");
     if ((c == '?' || c == '-') && is_blankz(pk(p, 1)))
-        return p_fail(p, YAML_SCANNER_ERROR, c == '?' ? "complex mapping keys are not supported"
+        return p_fail(p, YAML_SCANNER_ERROR, c == '?' ? "a complex mapping key is not allowed in this context"
                                                       : "block sequence entries are not allowed in this context");
     if (c == ':' && is_blankz(pk(p, 1)))
         return p_fail(p, YAML_SCANNER_ERROR, "mapping values are not allowed in this context");
@@ -531,9 +531,18 @@ static int parse_flow_map(P *p)
     for (;;) {
         if (!skip_flow_space(p)) return 0;
         if (pk(p, 0) == '}') { p_adv(p); break; }
-        int q = (pk(p, 0) == '\'' || pk(p, 0) == '"');
-        if (pk(p, 0) == ':' && (is_blankz(pk(p, 1)) || is_flowind(pk(p, 1)))) {
-            if (!p_empty(p)) return 0;       /* {: v} */
+        int complex_key = 0;
+        if (pk(p, 0) == '?' && is_blankz(pk(p, 1))) {        /* {? key : value} */
+            complex_key = 1;
+            p_adv(p);
+            if (!skip_flow_space(p)) return 0;
+        }
+        int q = (pk(p, 0) == '\'' || pk(p, 0) == '"') || complex_key;
+        if ((pk(p, 0) == ':' && (is_blankz(pk(p, 1)) || is_flowind(pk(p, 1)))) ||
+            (complex_key && (pk(p, 0) == ',' || pk(p, 0) == '}'))) {
+            if (!p_empty(p)) return 0;       /* {: v}, {? } */
+        } else if (complex_key) {
+            if (!parse_flow_node(p)) return 0;
         } else {
             const size_t key_line = p->line;
             if (!parse_flow_node(p)) return 0;
@@ -614,12 +623,38 @@ static int parse_block_map(P *p, size_t n, int style)
     e->data.mapping_start.style = YAML_BLOCK_MAPPING_STYLE;
     e->start_mark.column = e->end_mark.column = n;
     for (;;) {
-        if (!p_scalar(p, p->sc, p->sc_n, (yaml_scalar_style_t)style)) return 0;
-        p_adv(p);                                   /* ':' */
-        if (!parse_map_value(p, n)) return 0;
+        if (style >= 0) {
+            if (!p_scalar(p, p->sc, p->sc_n, (yaml_scalar_style_t)style)) return 0;
+            p_adv(p);                               /* ':' */
+            if (!parse_map_value(p, n)) return 0;
+        } else {
+            /* complex key: "? key" and, on a line of its own at the same indent, ": value" */
+            p->plain_indent = n + 1;
+            p_adv(p);                               /* '?' */
+            skip_line_tail(p);
+            if (at_line_end(p)) {
+                if (!skip_to_content(p)) return 0;
+                if (!at_eof(p) && !at_marker(p) && p->col > n) { if (!parse_block_node(p)) return 0; }
+                else if (!p_empty(p)) return 0;
+            } else if (!parse_block_node(p)) return 0;
+            if (!skip_to_content(p)) return 0;
+            if (!at_eof(p) && !at_marker(p) && p->col == n && pk(p, 0) == ':' && is_blankz(pk(p, 1))) {
+                p->plain_indent = n + 1;
+                p_adv(p);                           /* ':' */
+                skip_line_tail(p);
+                if (at_line_end(p)) {
+                    if (!skip_to_content(p)) return 0;
+                    if (!at_eof(p) && !at_marker(p) && p->col > n) { if (!parse_block_node(p)) return 0; }
+                    else if (!at_eof(p) && !at_marker(p) && p->col == n && pk(p, 0) == '-' && is_blankz(pk(p, 1))) {
+                        if (!parse_block_seq(p, n, 1)) return 0;
+                    } else if (!p_empty(p)) return 0;
+                } else if (!parse_block_node(p)) return 0;
+            } else if (!p_empty(p)) return 0;
+        }
         if (!skip_to_content(p)) return 0;
         if (at_eof(p) || at_marker(p) || p->col < n) break;
         if (p->col > n) return p_fail(p, YAML_PARSER_ERROR, "did not find expected key (bad indentation of a mapping entry)");
+        if (pk(p, 0) == '?' && is_blankz(pk(p, 1))) { style = -1; continue; }
         if (pk(p, 0) == '[' || pk(p, 0) == '{')
             return p_fail(p, YAML_PARSER_ERROR, "flow collections as mapping keys are not supported");
         const size_t key_line = p->line;
@@ -664,6 +699,7 @@ static int parse_block_node(P *p)
     int c = pk(p, 0), style;
     size_t col = p->col;
     if (c == '-' && is_blankz(pk(p, 1))) return parse_block_seq(p, col, 0);
+    if (c == '?' && is_blankz(pk(p, 1))) return parse_block_map(p, col, -1);
     if (c == '[' || c == '{') {
         if (!(c == '[' ? parse_flow_seq(p) : parse_flow_map(p))) return 0;
         skip_line_tail(p);
