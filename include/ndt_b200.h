@@ -115,6 +115,14 @@ int ndt_b200_upload(ndt_b200_ctx *ctx, const ndt_flat_scene *fs);
 #define NDT_B200_OPT_FUSED 2u         /* one fused kernel per bounce generation instead of the trace/shade wavefront (A/B measurements) */
 int ndt_b200_set_options(ndt_b200_ctx *ctx, uint32_t options);
 
+/* Sizing of the per-render ray pools.  A pass over n0 primary slots gets a record pool of
+ * n0 * (1 + bounce_factor) + slack_records entries (defaults 6.0 and 65536) and works a generation off in
+ * batches of at most rays_per_batch rays (default 2^23; rounded up to a multiple of 32; 0 = default).
+ * ndt_b200_render_tile recovers from an exhausted pool by halving the tile (a single row that still does
+ * not fit is retried once with a larger pool), so small values are safe, only slower -- the tests use them
+ * to exercise exactly that recovery and the batching of the device-side generation loop. */
+int ndt_b200_set_pool(ndt_b200_ctx *ctx, double bounce_factor, int slack_records, int rays_per_batch);
+
 /* Render the tile [x0,x0+tw) x [y0,y0+th) of the uploaded frame into HOST
  * buffers laid out tile-row-major (tw*th elements): fp64 RGBA as render_line
  * stores it (ndt.c:752, image.h:22-26), 8-bit RGBA through pixel_d2c
@@ -125,10 +133,13 @@ int ndt_b200_render_tile(ndt_b200_ctx *ctx, int x0, int y0, int tw, int th,
                          double *rgba_f64, uint8_t *rgba_u8, uint8_t *hit,
                          int32_t *obj_id, double *inv_depth, ndt_b200_stats *stats);
 
-/* Same, but the outputs are DEVICE pointers and the work is only enqueued on
- * `cuda_stream` (a cudaStream_t, NULL = the context's stream).  Statistics
- * are available from ndt_b200_last_stats() after the stream is synchronised
- * by ndt_b200_sync(). */
+/* Same, but the outputs are DEVICE pointers and the work is only enqueued on the
+ * context's stream (ndt_b200_stream): one small kernel and ONE CUDA-graph launch per
+ * frame -- the loop over bounce generations runs on the device -- so the call returns
+ * without waiting for the GPU.  What goes wrong inside the frame (ray pool exhausted:
+ * NDT_B200_E_OVERFLOW) is therefore reported by ndt_b200_sync(), which also makes the
+ * statistics available to ndt_b200_last_stats(); this entry point does not retry --
+ * render a smaller tile, or use ndt_b200_render_tile, which does. */
 int ndt_b200_launch_tile(ndt_b200_ctx *ctx, int x0, int y0, int tw, int th,
                          void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
                          void *d_obj_id, void *d_inv_depth);

@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NDT_B200_LIB") or os.path.join(_HERE, "libndt_b200.so")
 
 OPT_COUNT_FLOPS = 1
+OPT_FUSED = 2
 
 
 class NdtB200Error(RuntimeError):
@@ -96,6 +97,7 @@ def lib():
     L.ndt_b200_destroy.restype = None
     L.ndt_b200_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.ndt_b200_set_options.argtypes = [C.c_void_p, C.c_uint32]
+    L.ndt_b200_set_pool.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
     L.ndt_b200_render_tile.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5 + [C.POINTER(Stats)]
     L.ndt_b200_launch_tile.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5
     L.ndt_b200_sync.argtypes = [C.c_void_p]
@@ -265,6 +267,10 @@ class Context:
 
     def set_options(self, options):
         _check(lib().ndt_b200_set_options(self._h, options))
+
+    def set_pool(self, bounce_factor=6.0, slack_records=65536, rays_per_batch=0):
+        """ndt_b200_set_pool: record pool = n0 * (1 + bounce_factor) + slack_records, batches of rays_per_batch."""
+        _check(lib().ndt_b200_set_pool(self._h, bounce_factor, slack_records, rays_per_batch))
 
     def upload(self, flat):
         self._flat = flat  # keep the bytes alive until the async copy is consumed

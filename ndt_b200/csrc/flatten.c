@@ -835,6 +835,25 @@ done:
 
 void ndt_b200_free_flat(ndt_flat_scene *fs) { free(fs); }
 
+/* doubles of an object's geometry block (layouts in ndt_flat.h; the device's copy is geom_block_doubles, warp.cuh) */
+static int flat_geom_doubles(int type, int m, int np)
+{
+    switch (type) {
+    case NDT_T_SPHERE: return np + 1;
+    case NDT_T_HPLANE: return 2 * np;
+    case NDT_T_HDISK: return 2 * np + 1;
+    case NDT_T_ORTHOTOPE: return np + m * np + 3 * m;
+    case NDT_T_FACET: return 6 * np + 7;
+    case NDT_T_HFACET: return 6 * np + 5;
+    case NDT_T_CYLINDER: return 2 * np + 4;
+    case NDT_T_HCYLINDER: return np + m * np + 3 * m + 1;
+    }
+    return 0;
+}
+
+/* `bytes` is what the caller can vouch for: a blob read from disk or received from another rank passes its
+ * length; the in-memory entry points (ndt_b200_upload) pass header.total_bytes, i.e. THEIR caller guarantees
+ * that many readable bytes (include/ndt_b200.h) */
 int ndt_b200_flat_validate(const void *blob, size_t bytes)
 {
     const ndt_flat_header *h = blob;
@@ -874,12 +893,47 @@ int ndt_b200_flat_validate(const void *blob, size_t bytes)
              ob[i].child_begin + ob[i].child_count > h->n_objects))
             return ndt_set_error(NDT_B200_E_ARG, "flat scene: hcube %d children out of range", i);
     }
+    /* every geometry block the kernels follow an offset into lies inside geom[] */
+    for (int i = 0; i < h->n_objects; ++i) {
+        const uint64_t nd_ = (uint64_t)flat_geom_doubles(ob[i].type, ob[i].n_axes, (int)np);
+        if ((uint64_t)ob[i].geom_off + nd_ > h->n_geom)
+            return ndt_set_error(NDT_B200_E_ARG, "flat scene: geometry of object %d outside geom[]", i);
+    }
+    const ndt_flat_light *lt = NDT_FLAT_PTR(blob, const ndt_flat_light, h->off_lights);
+    for (int i = 0; i < h->n_lights; ++i) {
+        if (lt[i].type < NDT_L_AMBIENT || lt[i].type > NDT_L_SPOT)
+            return ndt_set_error(NDT_B200_E_ARG, "flat scene: light %d has type %d", i, lt[i].type);
+        /* pos, dir, rev_unit, near_off: 4 npad doubles (ndt_flat_light::vec_off) */
+        if ((uint64_t)lt[i].vec_off + 4 * np > h->n_geom)
+            return ndt_set_error(NDT_B200_E_ARG, "flat scene: vectors of light %d outside geom[]", i);
+    }
+    /* nodes are stored in pre-order: a child's index is larger than its parent's, which rules out cycles;
+     * the walk below recomputes what the traversal stack and the leaf staging are sized by */
     const ndt_flat_node *nd = NDT_FLAT_PTR(blob, const ndt_flat_node, h->off_nodes);
+    int max_leaf = 0;
     for (int i = 0; i < h->n_nodes; ++i) {
         if (nd[i].dim >= h->n || nd[i].left >= h->n_nodes || nd[i].right >= h->n_nodes ||
             nd[i].left < -1 || nd[i].right < -1 || nd[i].leaf_count < 0 || nd[i].leaf_begin < 0 ||
-            nd[i].leaf_begin + nd[i].leaf_count > h->n_leaf_refs)
+            nd[i].leaf_begin + nd[i].leaf_count > h->n_leaf_refs ||
+            (nd[i].left >= 0 && nd[i].left <= i) || (nd[i].right >= 0 && nd[i].right <= i))
             return ndt_set_error(NDT_B200_E_ARG, "flat scene: kd node %d malformed", i);
+        if (nd[i].leaf_count > max_leaf) max_leaf = nd[i].leaf_count;
+    }
+    if (h->n_nodes > 0) {
+        /* depth by one forward pass (children come after their parent) */
+        int *depth = calloc((size_t)h->n_nodes, sizeof *depth);
+        if (!depth) return ndt_set_error(NDT_B200_E_NOMEM, "out of memory");
+        int deepest = 0;
+        for (int i = 0; i < h->n_nodes; ++i) {
+            if (depth[i] > deepest) deepest = depth[i];
+            if (nd[i].dim < 0) continue;
+            if (nd[i].left >= 0 && depth[nd[i].left] < depth[i] + 1) depth[nd[i].left] = depth[i] + 1;
+            if (nd[i].right >= 0 && depth[nd[i].right] < depth[i] + 1) depth[nd[i].right] = depth[i] + 1;
+        }
+        free(depth);
+        if (deepest > h->tree_depth || max_leaf > h->max_leaf)
+            return ndt_set_error(NDT_B200_E_ARG, "flat scene: header says depth %d / largest leaf %d, the nodes say %d / %d",
+                                 h->tree_depth, h->max_leaf, deepest, max_leaf);
     }
     const int32_t *lr = NDT_FLAT_PTR(blob, const int32_t, h->off_leaf_refs);
     for (int i = 0; i < h->n_leaf_refs; ++i)

@@ -328,64 +328,125 @@ __device__ __forceinline__ void hit_load(const HitRec *src, double &t, int &id, 
     t = a.x; id = __double2loint(a.y); win = __double2hiint(a.y); found = __double2loint(b.x);
 }
 
-struct WaveArgs {
-    int gen;                 /* 0: rays are generated from pixels */
-    int start, count;        /* this generation's slots are [start, start+count) */
-    int n0;                  /* slots of generation 0 (tile padded to 8x4 blocks) */
+/* ---- the generation loop lives on the device -------------------------------------------------------
+ * Everything a launch needs to know about "which rays now" is read from WaveState in device memory, so the
+ * host can enqueue a whole frame without knowing how many bounce generations it has: one CUDA graph per
+ * frame whose body is a WHILE node (kernels.cu), or -- same kernels -- a host loop that reads `cont` back.
+ * A generation larger than gen_cap is worked off in batches (the shadow queue and its answers are sized
+ * for one batch).  Three groups of fields, each on its own cache lines: constant for a pass (k_begin),
+ * constant for a launch (k_begin / k_next_gen), and the atomics of the running launch. */
+constexpr int WAVE_MAX_GEN = 1024;
+struct WaveState {
+    /* the pass: written by k_begin */
+    int n0;                  /* slots of generation 0 (tile padded to 8x4 blocks, or the sample count) */
+    int x0, y0, tw, th, bpr; /* tile, and 8-pixel blocks per tile row (0: an explicit sample list) */
+    int eye;                 /* eye_override of primary_ray (ANAGLYPH_3D passes) */
+    int first;
+    const double *samples_xy; /* generation 0 from an explicit list of pixel-space positions (ip, jp) instead of the
+                                 tile's pixel grid: the sub-pixel samples of the recursive anti-aliasing */
+    uint8_t *out_hit;
+    int32_t *out_id;
+    double *out_depth;
+    double *out_f64;
+    uint8_t *out_u8;
+    /* the launch: written by k_begin and k_next_gen / k_resolve_next, read-only for every other kernel */
+    alignas(128) int gen;    /* generation of the current batch; 0: rays are generated from pixels */
+    int start, count;        /* the batch: record slots [start, start + count) */
+    int gen_start, gen_count; /* the generation the batch belongs to */
+    int ngen;                /* finished generations (gstart / gcount filled) */
+    int iters;               /* batches worked off */
+    int cont;                /* the loop goes on (mirror of the WHILE node's condition, for the host loop) */
+    int resolve_g;           /* the generation k_resolve folds next */
+    int fail;                /* copy of pool_overflow | kd_fault << 8 when the loop ended */
+    /* atomics of the running launch */
+    alignas(128) int tail;   /* next free record slot */
+    int next0;               /* work counter, radiance rays */
+    int stail;               /* shadow queue tail */
+    int next1;               /* work counter, shadow queries */
+    int pool_overflow;       /* 1 record pool, 2 shadow queue, 3 more than WAVE_MAX_GEN generations */
+    int kd_fault;            /* 1 traversal stack overflow, 2 staging copy timed out */
+    alignas(128) int gstart[WAVE_MAX_GEN];
+    int gcount[WAVE_MAX_GEN];
+};
+
+struct WaveArgs {            /* constant for the life of a graph: pool pointers and capacities */
     int cap;                 /* record pool capacity */
-    int x0, y0, tw, th, bpr; /* tile, and 8-pixel blocks per tile row */
+    int gen_cap;             /* rays per batch (multiple of 32) */
+    int scap;                /* shadow queue capacity (gen_cap * non-ambient lights) */
+    int pad;
     RayRec *rec;
     void *rays;              /* RayIn<NP>[cap - n0], slot s lives at rays[s - n0] */
     HitRec *hits;            /* [cap], by slot */
     void *srays;             /* shadow queries RayIn<NP>[scap]: frac = dist_limit, depth = 1 + light index for the
                                 any-hit query of a DIRECTIONAL light, else 0 */
-    HitRec *shits;           /* [count * n_lights]: the answer to the shadow query of (ray, light) at [ray * n_lights + light];
-                                the query carries that index (ray_aux), so k_shade<B> reads its answers without an
-                                indirection and can start all of them at once (entries without a query are never read) */
-    int *sslot;              /* unused */
-    int scap;
-    int *ctr;                /* [0] tail [1] next (radiance) [2] pool overflow [3] kd overflow / staging fault
-                                [4] shadow tail [5] next (shadow) */
-    unsigned long long *stats; /* [0] shadow rays [1] flops [2] rays_ref [3] samples [4] hit pixels */
+    HitRec *shits;           /* [gen_cap * n_lights]: the answer to the shadow query of (ray, light) at [ray * n_lights + light],
+                                ray counted from the start of the batch; the query carries that index (ray_aux), so
+                                k_shade<B> reads its answers without an indirection (entries without a query are never read) */
+    WaveState *st;
+    unsigned long long *stats; /* [0] shadow rays [1] flops [2] rays_ref [3] samples [4] hit pixels [5] traced pixels */
+    uint32_t *mb_bits;
+    uint32_t mb_stride, mb_words, mb_shift, pad2;
+    const void *leafrec;
+    const void *boxrec;
+};
+
+/* what k_begin gets by value */
+struct WaveBegin {
+    int n0, x0, y0, tw, th, bpr, eye, first;
+    const double *samples_xy;
     uint8_t *out_hit;
     int32_t *out_id;
     double *out_depth;
-    uint32_t *mb_bits;
-    uint32_t mb_stride, mb_words, mb_shift;
-    const void *leafrec;
-    const void *boxrec;
-    const double *samples_xy; /* generation 0 from an explicit list of pixel-space positions (ip, jp) instead of the
-                                 tile's pixel grid: the sub-pixel samples of the recursive anti-aliasing */
+    double *out_f64;
+    uint8_t *out_u8;
 };
 
-/* the ray of slot r of this generation */
+/* WaveState fields are read where they are used: an ordinary load is hoisted to the top of the function by the
+ * compiler and then lives in a register across the whole shading code (+40-60 registers measured); a volatile
+ * load stays where it is written */
+template <class T> __device__ __forceinline__ T ld_here(const T *p) { return *(const volatile T *)p; }
+template <class T> __device__ __forceinline__ T *ld_here(T *const *p) { return (T *)*(T *const volatile *)p; }
+
+/* the ray of slot start + r of the current batch */
 template <int NP>
-__device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, int r, int lane, double *o, double *v,
-                                         double &frac, int &depth, int &tx, int &ty)
+__device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, const WaveState *st, int gen, int start, int count,
+                                         int r, int lane, double *o, double *v, double &frac, int &depth, int &tx, int &ty)
 {
-    bool active = r < a.count;
+    bool active = r < count;
     frac = 1.0;
     depth = sc.max_optic_depth;
     tx = ty = 0;
-    if (a.gen == 0 && a.samples_xy) {
-        if (active) primary_ray_at<NP>(sc, a.samples_xy[2 * (size_t)r], a.samples_xy[2 * (size_t)r + 1], o, v);
-    } else if (a.gen == 0) {
-        const int blk = r >> 5;
-        tx = (blk % a.bpr) * 8 + (lane & 7);
-        ty = (blk / a.bpr) * 4 + (lane >> 3);
-        active = active && tx < a.tw && ty < a.th;
-        if (active) active = primary_ray<NP>(sc, a.x0 + tx, a.y0 + ty, o, v);
+    if (gen == 0) {
+        const double *sxy = ld_here(&st->samples_xy);
+        const int s = start + r;
+        if (sxy) {
+            if (active) primary_ray_at<NP>(sc, sxy[2 * (size_t)s], sxy[2 * (size_t)s + 1], o, v);
+        } else {
+            const int blk = s >> 5, bpr = ld_here(&st->bpr);
+            tx = (blk % bpr) * 8 + (lane & 7);
+            ty = (blk / bpr) * 4 + (lane >> 3);
+            active = active && tx < ld_here(&st->tw) && ty < ld_here(&st->th);
+            if (active) active = primary_ray<NP>(sc, ld_here(&st->x0) + tx, ld_here(&st->y0) + ty, o, v, ld_here(&st->eye));
+        }
     } else if (active) {
-        ray_load<NP>((const RayIn<NP> *)a.rays + (a.start + r - a.n0), o, v, frac, depth);
+        ray_load<NP>((const RayIn<NP> *)a.rays + (start + r - ld_here(&st->n0)), o, v, frac, depth);
     }
     return active;
 }
 
-/* MODE 0: the generation's own rays, MODE 1: its shadow queries */
+/* MODE 0: the batch's own rays, MODE 1: its shadow queries */
 template <int NP, int MODE>
 __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Scene sc, const WaveArgs a)
 {
     const int lane = threadIdx.x & 31;
+    WaveState *st = a.st;
+    const int gen = st->gen, start = st->start;
+    int count = st->count;
+    if (MODE == 1) {             /* written by k_shade<A>, complete before this launch started */
+        count = *(volatile const int *)&st->stail;
+        if (count > a.scap) count = a.scap;
+    }
+    if ((int)(blockIdx.x * blockDim.x) >= count && blockIdx.x > 0) return;   /* the grid is sized for a full batch */
     Mailbox mb;
     mb.bits = a.mb_bits; mb.stride = a.mb_stride;
     mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,12 +456,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
     WarpStage<NP> ws;
     ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
     int kd_overflow = 0;
-    int count = a.count;
-    if (MODE == 1) {             /* written by k_shade<A>, complete before this launch started */
-        count = *(volatile const int *)(a.ctr + 4);
-        if (count > a.scap) count = a.scap;
-    }
-    int *next = a.ctr + (MODE ? 5 : 1);
+    int *next = MODE ? &st->next1 : &st->next0;
 
     while (true) {
         /* (fetching the counter one batch ahead was measured slower: profiles/r01_experiments.md) */
@@ -415,7 +471,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         int dest = 0;                /* MODE 1: index of the answer in shits[] */
         if (MODE == 0) {
             double frac; int depth, tx, ty;
-            want = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
+            want = wave_ray<NP>(sc, a, st, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
         } else {
             want = r < count;
             if (want) {
@@ -428,44 +484,43 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         Hit T;
         trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
         if (ws.fault) break;     /* warp-uniform (warp.cuh) */
-        if (want) hit_store(MODE == 0 ? a.hits + (a.start + r) : a.shits + dest, T.t, T.id, T.win, T.found);
+        if (want) hit_store(MODE == 0 ? a.hits + (start + r) : a.shits + dest, T.t, T.id, T.win, T.found);
     }
-    if (kd_overflow) atomicMax(a.ctr + 3, 1);
-    if (ws.fault) atomicMax(a.ctr + 3, 2);
+    if (kd_overflow) atomicMax(&st->kd_fault, 1);
+    if (ws.fault) atomicMax(&st->kd_fault, 2);
 }
 
-/* PHASE 0 = A (emit the shadow queries), PHASE 1 = B (consume the answers, finish the ray) */
-template <int NP, int PHASE>
-#ifdef NDT_SHADE_MIN_BLOCKS
-__global__ void __launch_bounds__(BLOCK, NDT_SHADE_MIN_BLOCKS) k_shade(
-#else
-/* no register cap: measured per dimension, a cap that helps NP=4 (3 CTA/SM) costs NP=10 more than it gains */
-__global__ void __launch_bounds__(BLOCK) k_shade(
+/* PHASE 0 = A (emit the shadow queries), PHASE 1 = B (consume the answers, finish the ray): one ray of the
+ * batch per thread. */
+#ifndef NDT_SHADE_LOOP
+#define NDT_SHADE_LOOP 1      /* 1: fixed grid striding over the batch; 0: one thread per ray of a FULL batch, early exit */
 #endif
-const Scene sc, const WaveArgs a)
+template <int NP, int PHASE>
+__device__ __forceinline__ void shade_one(
+const Scene &sc, const WaveArgs &a, WaveState *st, int r, int lane,
+                                       unsigned long long &shadow_total)
 {
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;     /* the grid covers count rounded up to whole warps */
+    const int gen = st->gen, start = st->start, count = st->count;
+    const int nl = sc.n_lights;
     double o[NP], v[NP], frac;
     int depth, tx, ty;
     /* the kernel is bound by the latency of its first loads (ncu: long_scoreboard at the first use of the
      * hit record): start them before the ray is rebuilt */
     Hit T0;
     T0.t = -1; T0.id = -1; T0.win = -1; T0.found = 0;
-    if (r < a.count) hit_load(a.hits + (a.start + r), T0.t, T0.id, T0.win, T0.found);
+    if (r < count) hit_load(a.hits + (start + r), T0.t, T0.id, T0.win, T0.found);
     /* phase B: the answers of the first lights as well (k_shade is latency bound: ncu long_scoreboard 41 %,
      * the slot -> answer chain of every light was on the critical path) */
     constexpr int PF = 3;
     Hit P[PF];
-    const int nl = sc.n_lights;
     if (PHASE == 1) {
         NDT_UNROLL
         for (int k = 0; k < PF; ++k) {
             P[k].t = -1; P[k].id = -1; P[k].win = -1; P[k].found = 0;
-            if (r < a.count && k < nl) hit_load(a.shits + ((size_t)r * nl + k), P[k].t, P[k].id, P[k].win, P[k].found);
+            if (r < count && k < nl) hit_load(a.shits + ((size_t)r * nl + k), P[k].t, P[k].id, P[k].win, P[k].found);
         }
     }
-    const bool active = wave_ray<NP>(sc, a, r, lane, o, v, frac, depth, tx, ty);
+    const bool active = wave_ray<NP>(sc, a, st, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
     Tally<false> none;
     Shade<NP> S;
     RayRec rec;
@@ -487,7 +542,7 @@ const Scene sc, const WaveArgs a)
                 const unsigned b = __ballot_sync(FULL, want);
                 int wbase = 0;
                 if (b) {
-                    if (lane == 0) wbase = atomicAdd(a.ctr + 4, __popc(b));
+                    if (lane == 0) wbase = atomicAdd(&st->stail, __popc(b));
                     wbase = __shfl_sync(FULL, wbase, 0);
                 }
                 if (active) {
@@ -499,7 +554,7 @@ const Scene sc, const WaveArgs a)
                             ray_store<NP>((RayIn<NP> *)a.srays + slot, S.ro, S.rv, S.limit,
                                           S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0, r * nl + it);
                         } else {
-                            atomicExch(a.ctr + 2, 1);   /* the render fails with NDT_B200_E_OVERFLOW */
+                            atomicExch(&st->pool_overflow, 2);   /* the render fails with NDT_B200_E_OVERFLOW */
                         }
                     }
                 }
@@ -528,13 +583,15 @@ const Scene sc, const WaveArgs a)
     const int total = __popc(b1) + __popc(b2);
     int wbase = 0;
     if (total > 0) {
-        if (lane == 0) wbase = atomicAdd(a.ctr, total);
+        if (lane == 0) wbase = atomicAdd(&st->tail, total);
         wbase = __shfl_sync(FULL, wbase, 0);
     }
     const bool fits = wbase + total <= a.cap;
-    if (total > 0 && !fits && lane == 0) atomicExch(a.ctr + 2, 1);
+    if (total > 0 && !fits && lane == 0) atomicExch(&st->pool_overflow, 1);
     const unsigned lt = (1u << lane) - 1u;
     RayIn<NP> *rays = (RayIn<NP> *)a.rays;
+    const int n0 = ld_here(&st->n0);
+    const bool pixels = gen == 0 && ld_here(&st->samples_xy) == nullptr;
     if (active) {
         if (sp.want_refl == 2) rec.child_refl = CHILD_BLACK;
         if (sp.want_refr == 2) rec.child_refr = CHILD_BLACK;
@@ -542,38 +599,77 @@ const Scene sc, const WaveArgs a)
             const int s = wbase + __popc(b1 & lt);
             rec.child_refl = fits ? s : CHILD_BLACK;
             if (fits) {
-                ray_store<NP>(rays + (s - a.n0), sp.origin, sp.refl_dir, sp.refl_frac, depth - 1);
+                ray_store<NP>(rays + (s - n0), sp.origin, sp.refl_dir, sp.refl_frac, depth - 1);
             }
         }
         if (q2) {
             const int s = wbase + __popc(b1) + __popc(b2 & lt);
             rec.child_refr = fits ? s : CHILD_BLACK;
             if (fits) {
-                ray_store<NP>(rays + (s - a.n0), sp.origin, sp.refr_dir, sp.refr_frac, depth - 1);
+                ray_store<NP>(rays + (s - n0), sp.origin, sp.refr_dir, sp.refr_frac, depth - 1);
             }
         }
-        rec_store(a.rec + (a.start + r), rec);
-        if (a.gen == 0 && !a.samples_xy) {
-            const size_t p = (size_t)ty * a.tw + tx;
-            if (a.out_hit) a.out_hit[p] = (uint8_t)p_hit;
-            if (a.out_id) a.out_id[p] = p_id;
-            if (a.out_depth) a.out_depth[p] = (p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
+        rec_store(a.rec + (start + r), rec);
+        if (pixels) {
+            const size_t p = (size_t)ty * ld_here(&st->tw) + tx;
+            uint8_t *oh = ld_here(&st->out_hit);
+            int32_t *oi = ld_here(&st->out_id);
+            double *od = ld_here(&st->out_depth);
+            if (oh) oh[p] = (uint8_t)p_hit;
+            if (oi) oi[p] = p_id;
+            if (od) od[p] = (p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
         }
-    } else if (a.gen == 0 && r < a.count) {
+    } else if (gen == 0 && r < count) {
         /* padding lane of a partial 8x4 block: keep the record defined */
         RayRec z;
         z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
         z.h[0] = z.h[1] = z.h[2] = 0.0;
         z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
-        rec_store(a.rec + (a.start + r), z);
-        if (!a.samples_xy && tx < a.tw && ty < a.th) {       /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
-            const size_t p = (size_t)ty * a.tw + tx;
-            if (a.out_hit) a.out_hit[p] = 0;
-            if (a.out_id) a.out_id[p] = -1;
-            if (a.out_depth) a.out_depth[p] = 0.0;
+        rec_store(a.rec + (start + r), z);
+        if (pixels && tx < ld_here(&st->tw) && ty < ld_here(&st->th)) {   /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
+            const size_t p = (size_t)ty * ld_here(&st->tw) + tx;
+            uint8_t *oh = ld_here(&st->out_hit);
+            int32_t *oi = ld_here(&st->out_id);
+            double *od = ld_here(&st->out_depth);
+            if (oh) oh[p] = 0;
+            if (oi) oi[p] = -1;
+            if (od) od[p] = 0.0;
         }
     }
-    unsigned long long shadow_total = active ? nsh : 0;
+    shadow_total += active ? nsh : 0;
+}
+
+/* The grid is fixed (it sits in a CUDA graph); a warp strides over the batch.  Inside the striding loop ptxas
+ * hoists the loop-invariant scene loads (lights, materials) out of the loop and keeps them in registers: +40 to
+ * +60 registers, one CTA per SM less, k_shade<4,B> 3.3 -> 4.6 ms on BASELINE config 1 (profiles/r02_*).  The
+ * launch bounds pin each instantiation to the occupancy of its loop-free form (register counts of that form:
+ * 105 / 124 / 164 / 208 / 190 for phase A and 168 / 222 / 255 / 255 / 255 for phase B at NP = 4 ... 12). */
+template <int NP, int PHASE> __host__ __device__ constexpr int shade_min_blocks()
+{
+#ifdef NDT_SHADE_MIN_BLOCKS
+    return NDT_SHADE_MIN_BLOCKS;
+#else
+    return PHASE == 0 ? (NP <= 6 ? 4 : (NP <= 8 ? 3 : 2)) : (NP <= 4 ? 3 : 2);
+#endif
+}
+template <int NP, int PHASE>
+__global__ void __launch_bounds__(BLOCK, shade_min_blocks<NP, PHASE>()) k_shade(
+const Scene sc, const WaveArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int count = a.st->count;
+    unsigned long long shadow_total = 0;
+#if NDT_SHADE_LOOP
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r - lane < count; r += gridDim.x * blockDim.x)
+        shade_one<NP, PHASE>(sc, a, a.st, r, lane, shadow_total);
+#else
+    {
+        const int r = blockIdx.x * blockDim.x + threadIdx.x;
+        if (r - lane >= count) return;
+        shade_one<NP, PHASE>(sc, a, a.st, r, lane, shadow_total);
+    }
+#endif
+    if (PHASE == 0) return;
     for (int d = 16; d > 0; d >>= 1) shadow_total += __shfl_down_sync(FULL, shadow_total, d);
     if (lane == 0 && shadow_total) atomicAdd(&a.stats[0], shadow_total);
 }
@@ -629,6 +725,7 @@ struct NpOps {
     int (*trace_blocks_per_sm)(bool boxed);
     void (*trace)(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
     void (*shade)(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
+
     int (*blocks_per_sm)(bool cnt, bool boxed);
     void (*generation)(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a);
     void (*pack_leaf)(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out);
@@ -636,5 +733,10 @@ struct NpOps {
                        const double *limits, int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
                        uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
                        const void *leafrec, const void *boxrec);
+    /* for the graph nodes of the device-side generation loop (kernels.cu) */
+    const void *(*trace_fn)(int mode);
+    const void *(*shade_fn)(int phase);
+    size_t (*trace_smem_bytes)(bool boxed);
+    int (*shade_grid)(int sm_count, int gen_cap);   /* blocks of a k_shade launch */
 };
 const NpOps *ndt_np_ops(int np);     /* NULL: dimension not built */

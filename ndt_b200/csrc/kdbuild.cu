@@ -30,12 +30,14 @@
 #include <string.h>
 #include <stdio.h>
 #include <time.h>
+#include <pthread.h>
 #include "ndt_abi.h"
 #include "ndt_internal.h"
 
 #define EPS NDT_EPS
 #define KD_GPU_MIN_ITEMS 48      /* below this the host scores the node itself */
 #define KD_BLOCK 256
+#define NDT_KD_MAX_DEVICES 64
 
 /* kd-tree.h:22-26, 40-43 */
 typedef struct {
@@ -160,10 +162,13 @@ static bool gpu_search(Builder &B, const int *list, int n, int *out_dim, double 
     const int blocks_per_dim = (per_dim + KD_BLOCK - 1) / KD_BLOCK;
     const int blocks = blocks_per_dim * B.dims;
     if ((size_t)n > B.list_cap || (size_t)blocks > B.best_cap) { B.err = "kd build: scratch too small"; return false; }
-    cudaMemcpyAsync(B.d_list, list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, B.st);
-    k_kd_score<<<blocks, KD_BLOCK, 0, B.st>>>(B.d_lo, B.d_hi, B.n_total, B.d_list, n, B.dims, B.d_best);
-    cudaMemcpyAsync(B.h_best, B.d_best, (size_t)blocks * sizeof(Best), cudaMemcpyDeviceToHost, B.st);
-    cudaError_t e = cudaStreamSynchronize(B.st);
+    cudaError_t e = cudaMemcpyAsync(B.d_list, list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, B.st);
+    if (e == cudaSuccess) {
+        k_kd_score<<<blocks, KD_BLOCK, 0, B.st>>>(B.d_lo, B.d_hi, B.n_total, B.d_list, n, B.dims, B.d_best);
+        e = cudaGetLastError();         /* a launch that never started leaves h_best stale: say so instead of decoding it */
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_best, B.d_best, (size_t)blocks * sizeof(Best), cudaMemcpyDeviceToHost, B.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(B.st);
     if (e != cudaSuccess) { B.err = cudaGetErrorString(e); return false; }
     Best b; b.score = INT_MIN; b.cand = INT_MAX;
     for (int k = 0; k < blocks; ++k) {
@@ -172,6 +177,7 @@ static bool gpu_search(Builder &B, const int *list, int n, int *out_dim, double 
     }
     if (b.score == INT_MIN) return false;
     const int side = b.cand & 1, rest = b.cand >> 1, d = rest / n, i = rest % n;
+    if (b.cand < 0 || d >= B.dims) { B.err = "kd build: the device returned a candidate outside the node"; return false; }
     *out_dim = d;
     *out_pos = side ? B.h_hi[(size_t)d * B.n_total + list[i]] + 2 * EPS
                     : B.h_lo[(size_t)d * B.n_total + list[i]] - 2 * EPS;
@@ -312,9 +318,17 @@ static int kd_build(void *tree_v, void *items_v, int max_depth, int leaf_size, d
     tree->obj_num = n;                                            /* kd-tree.c:470 */
 
     /* device scratch is kept for the life of the process (cudaMalloc / cudaFree /
-     * stream creation cost 10-300 ms, the build itself 17 ms for 6561 items) */
-    static struct { cudaStream_t st; double *d_lo, *d_hi; int *d_list; Best *d_best, *h_best;
-                    size_t vb, list_cap, best_cap; } K;
+     * stream creation cost 10-300 ms, the build itself 17 ms for 6561 items): one set PER DEVICE --
+     * the build runs on whichever device is current for the calling thread -- and one build at a time */
+    static struct Scratch { cudaStream_t st; double *d_lo, *d_hi; int *d_list; Best *d_best, *h_best;
+                            size_t vb, list_cap, best_cap; } Ks[NDT_KD_MAX_DEVICES];
+    static pthread_mutex_t kd_lock = PTHREAD_MUTEX_INITIALIZER;
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= NDT_KD_MAX_DEVICES)
+        return ndt_set_error(NDT_B200_E_CUDA, "ndt_b200_kd_tree_build: no usable current device");
+    struct Unlock { pthread_mutex_t *m; ~Unlock() { pthread_mutex_unlock(m); } } unlock_at_exit = { &kd_lock };
+    pthread_mutex_lock(&kd_lock);
+    Scratch &K = Ks[cur_dev];
     int rc = 0;
     struct timespec t0, t1, t2;
     clock_gettime(CLOCK_MONOTONIC, &t0);

@@ -1,23 +1,23 @@
 /*
- * kernels.cu -- wavefront kernels and the device half of the C ABI (ndt_b200.h).
+ * kernels.cu -- the host half of the wavefront and the device half of the C ABI (ndt_b200.h).
  *
- * One render = a loop over bounce generations:
- *   k_generation<NP>   persistent CTAs; every warp pulls 32 rays at a time from
- *                      the generation's queue (one atomicAdd per warp), traces
- *                      them (wave.cuh: nearest hit + lighting + shadow rays),
- *                      writes one RayRec per ray and appends the reflection /
- *                      refraction rays it spawned to the next generation's
- *                      queue; slots are handed out per warp with two ballots
- *                      and one atomicAdd.
- *   k_resolve          folds generation g+1 into g (deepest first), replaying
- *                      the reference's colour arithmetic in its own order.
- *   k_finish<>         generation 0 -> pixels: sample-loop replay (ndt.c:488),
- *                      fp64 RGBA as 2x16-byte stores, u8 RGBA as one 4-byte
- *                      store per pixel (pixel_d2c, image.h:36-39), statistics.
- *
- * Generation 0 maps a warp to an 8x4 pixel block so that the 32 primary rays
- * of a warp walk the same kd leaves.  fp64 arithmetic is never contracted
- * (-fmad=false) -- see core.cuh.
+ * One render = one pass over the tile's rays, generation by generation, with the loop ON THE DEVICE:
+ *   k_begin            resets WaveState (gen.cuh): generation 0 = the tile's pixels (8x4 blocks per warp)
+ *   WHILE (CUDA graph conditional node; condition set by k_next_gen)
+ *     k_trace<NP,0>    nearest hit of every ray of the batch            -> HitRec
+ *     k_shade<NP,A>    hit point, normal, side tests; one shadow query per light that needs one
+ *     k_trace<NP,1>    the shadow queries                                -> HitRec per (ray, light)
+ *     k_shade<NP,B>    the light loop in the reference's order, RayRec, reflection / refraction rays
+ *                      appended to the next generation (two ballots + one atomic per warp)
+ *     k_next_gen       next batch / next generation / stop
+ *   k_pre_resolve, WHILE { k_resolve, k_resolve_next }   fold generation g+1 into g, deepest first
+ *   k_finish           generation 0 -> pixels: sample-loop replay (ndt.c:488), fp64 RGBA as 2x16-byte
+ *                      stores, u8 RGBA as one 4-byte store per pixel (pixel_d2c, image.h:36-39)
+ * The host enqueues k_begin + ONE graph launch per frame and never waits inside a frame; errors (pool
+ * exhausted, traversal stack) are flags in WaveState that ndt_b200_sync reports.  Without graph support
+ * (or with NDT_B200_NO_GRAPH=1) the same kernels run from a host loop that reads `cont` back per batch.
+ * The fused k_generation path (NDT_B200_OPT_FUSED, the counting build) keeps its host loop.
+ * fp64 arithmetic is never contracted (-fmad=false) -- see core.cuh.
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -110,6 +110,146 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
     }
 }
 
+/* ---- bookkeeping kernels of the device-side generation loop (one thread each) ---- */
+__global__ void k_begin(WaveState *st, const WaveBegin b, int gen_cap, unsigned long long *stats)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    st->n0 = b.n0; st->x0 = b.x0; st->y0 = b.y0; st->tw = b.tw; st->th = b.th; st->bpr = b.bpr;
+    st->eye = b.eye; st->first = b.first;
+    st->samples_xy = b.samples_xy;
+    st->out_hit = b.out_hit; st->out_id = b.out_id; st->out_depth = b.out_depth;
+    st->out_f64 = b.out_f64; st->out_u8 = b.out_u8;
+    st->gen = 0; st->start = 0; st->count = b.n0 < gen_cap ? b.n0 : gen_cap;
+    st->gen_start = 0; st->gen_count = b.n0;
+    st->ngen = 0; st->iters = 0; st->cont = 1; st->resolve_g = 0; st->fail = 0;
+    st->tail = b.n0; st->next0 = 0; st->stail = 0; st->next1 = 0;
+    st->pool_overflow = 0; st->kd_fault = 0;
+    if (b.first) for (int k = 0; k < 8; ++k) stats[k] = 0ull;
+}
+
+/* after the four launches of a batch: the next batch of the generation, or the next generation, or the end.
+ * `h` is the condition of the graph's WHILE node (use_h = 0: launched from the host loop). */
+__global__ void k_next_gen(WaveState *st, int cap, int gen_cap, cudaGraphConditionalHandle h, int use_h)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int cont = 0;
+    st->iters += 1;
+    const int bend = st->start + st->count, gend = st->gen_start + st->gen_count;
+    if (st->pool_overflow || st->kd_fault) {
+        cont = 0;
+    } else if (bend < gend) {
+        st->start = bend;
+        st->count = (gend - bend) < gen_cap ? (gend - bend) : gen_cap;
+        cont = 1;
+    } else {
+        const int g = st->ngen;
+        st->gstart[g] = st->gen_start;
+        st->gcount[g] = st->gen_count;
+        st->ngen = g + 1;
+        int tail = st->tail;
+        if (tail > cap) tail = cap;          /* cannot happen without pool_overflow */
+        const int ncount = tail - gend;
+        if (ncount > 0) {
+            if (g + 1 >= WAVE_MAX_GEN) {
+                st->pool_overflow = 3;
+            } else {
+                st->gen += 1;
+                st->gen_start = gend; st->gen_count = ncount;
+                st->start = gend;
+                st->count = ncount < gen_cap ? ncount : gen_cap;
+                cont = 1;
+            }
+        }
+    }
+    st->next0 = 0; st->stail = 0; st->next1 = 0;
+    st->cont = cont;
+    if (!cont) st->fail = st->pool_overflow | (st->kd_fault << 8);
+    if (use_h) cudaGraphSetConditional(h, cont ? 1u : 0u);
+}
+
+/* between the two loops: the backward fold starts at the deepest generation */
+__global__ void k_pre_resolve(WaveState *st, cudaGraphConditionalHandle h, int use_h)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const int g = st->fail ? 0 : st->ngen - 1;
+    st->resolve_g = g;
+    if (use_h) cudaGraphSetConditional(h, g >= 1 ? 1u : 0u);
+}
+__global__ void k_resolve_next(WaveState *st, cudaGraphConditionalHandle h, int use_h)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const int g = st->resolve_g - 1;
+    st->resolve_g = g;
+    if (use_h) cudaGraphSetConditional(h, g >= 1 ? 1u : 0u);
+}
+
+/* the same two kernels for the device-side loop: what to fold comes from WaveState, the grids are fixed */
+__global__ void k_resolve_dev(RayRec *rec, const WaveState *st, int specular)
+{
+    if (st->fail) return;
+    const int g = st->resolve_g;
+    const int start = st->gstart[g], count = st->gcount[g];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        RayRec r;
+        rec_load(r, rec + start + i);
+        if (r.child_refl == CHILD_NONE && r.child_refr == CHILD_NONE) continue;
+        const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
+        const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
+        resolve_rec(r, c1, c2, specular);
+        rec_store(rec + start + i, r);
+    }
+}
+
+__global__ void k_finish_dev(RayRec *rec, const WaveState *st, int specular, unsigned long long *stats)
+{
+    if (st->fail) return;
+    const int tw = st->tw, th = st->th, bpr = st->bpr;
+    double *out_f64 = st->out_f64;
+    uint8_t *out_u8 = st->out_u8;
+    unsigned long long rays_ref = 0, samples = 0, hits = 0, traced = 0;
+    /* every warp runs the same number of iterations (the shuffles below need all 32 lanes) */
+    const int n = tw * th, np32 = (n + 31) & ~31;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np32; p += gridDim.x * blockDim.x) {
+        if (p >= n) continue;
+        const int tx = p % tw, ty = p / tw;
+        /* bpr == 0: a sample list, record r belongs to sample r */
+        const int slot = bpr ? ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7) : p;
+        RayRec r;
+        rec_load(r, rec + slot);
+        const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
+        const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
+        resolve_rec(r, c1, c2, specular);
+        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4] = { 0.0, 0.0, 0.0, 0.0 };
+        /* a pixel render_pixel leaves black without calling get_pixel_color has no sample loop */
+        const int ns = (r.flags & REC_UNTRACED) ? 0 : replay_samples(l, o);
+        if (out_f64) {
+            double2 *d = reinterpret_cast<double2 *>(out_f64 + 4 * (size_t)p);
+            d[0] = make_double2(o[0], o[1]);
+            d[1] = make_double2(o[2], o[3]);
+        }
+        if (out_u8) {
+            uchar4 c = make_uchar4(d2c(o[0]), d2c(o[1]), d2c(o[2]), d2c(o[3]));
+            reinterpret_cast<uchar4 *>(out_u8)[p] = c;
+        }
+        rays_ref += (unsigned long long)r.nrays * (unsigned long long)ns;
+        samples += (unsigned long long)ns;
+        hits += r.flags & 1u;
+        traced += (r.flags & REC_UNTRACED) ? 0 : 1;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        rays_ref += __shfl_down_sync(0xffffffffu, rays_ref, d);
+        samples += __shfl_down_sync(0xffffffffu, samples, d);
+        hits += __shfl_down_sync(0xffffffffu, hits, d);
+        traced += __shfl_down_sync(0xffffffffu, traced, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (rays_ref) atomicAdd(&stats[2], rays_ref);
+        if (samples) atomicAdd(&stats[3], samples);
+        if (hits) atomicAdd(&stats[4], hits);
+        if (traced) atomicAdd(&stats[5], traced);
+    }
+}
+
 /* FP64 pipe probe: 8 independent chains per thread */
 template <bool FUSED> __global__ void k_fp64_probe(double *sink, int iters)
 {
@@ -138,6 +278,17 @@ template <bool FUSED> __global__ void k_fp64_probe(double *sink, int iters)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return ndt_set_error(NDT_B200_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
+/* what ndt_b200_sync reads back of a pass: WaveState up to (not including) gstart[] */
+#define WAVE_HEAD_BYTES offsetof(WaveState, gstart)
+
+struct WaveGraph {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    int valid;
+    /* what the nodes were built from: rebuilt when any of it changes */
+    Scene sc; WaveArgs a; int np, n_sh, specular, trace_grid, shade_grid;
+};
+
 struct ndt_b200_ctx {
     int device;
     int sm_count;
@@ -155,17 +306,24 @@ struct ndt_b200_ctx {
     void *d_rays; size_t rays_bytes;
     uint32_t *d_mb; size_t mb_bytes;
     HitRec *d_hits; size_t hits_cap;     /* one per record slot */
-    char *d_srays; size_t srays_bytes;   /* shadow queries of one generation */
+    char *d_srays; size_t srays_bytes;   /* shadow queries of one batch */
     HitRec *d_shits; size_t shits_cap;
-    int *d_sslot; size_t sslot_cap;
     int trace_grid[2][8];                /* cached k_trace occupancy per (boxed scene, NP/2) */
     char *d_ana; size_t ana_bytes;       /* ANAGLYPH_3D: the two eyes' fp64 frames */
-    int *d_ctr;                          /* [0] tail [1] next [2..3] overflow [4] shadow tail [5] shadow next */
+    int *d_ctr;                          /* fused path: [0] tail [1] next [2..3] overflow */
+    WaveState *d_state;                  /* device-side generation loop (gen.cuh) */
     unsigned long long *d_stats;         /* 8 counters */
     int *h_ctr; unsigned long long *h_stats; /* pinned mirrors */
+    char *h_snap;                        /* pinned: WAVE_HEAD_BYTES per pass of the pending render (2) */
+    int n_snap;                          /* passes of the pending wavefront render; 0: none / the fused path */
+    int n_sh_pending;
+    WaveGraph wg;
+    int use_graph;                       /* 0: host loop (NDT_B200_NO_GRAPH=1, or the graph could not be built) */
     /* outputs for the host-buffer entry point */
     char *d_out; size_t out_cap;
-    double bounce_factor;
+    double bounce_factor;                /* record pool = n0 * (1 + bounce_factor) + pool_slack */
+    int pool_slack;
+    int gen_cap_max;                     /* rays per batch of the generation loop */
     uint32_t options;
     ndt_b200_stats last;
     int grid_blocks[4][8];               /* cached occupancy per (CNT + 2 * boxed scene, NP/2) */
@@ -225,7 +383,15 @@ extern "C" int ndt_b200_init(int device, ndt_b200_ctx **out)
     CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&c->h_ctr, 8 * sizeof(int)));
     CK(cudaMallocHost(&c->h_stats, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->d_state, sizeof(WaveState)));
+    CK(cudaMallocHost(&c->h_snap, 2 * WAVE_HEAD_BYTES));
     c->bounce_factor = 6.0;
+    c->pool_slack = 65536;
+    c->gen_cap_max = 1 << 23;
+    {
+        const char *e = getenv("NDT_B200_NO_GRAPH");
+        c->use_graph = !(e && *e && *e != '0');
+    }
     *out = c;
     return 0;
 }
@@ -236,9 +402,11 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
-    cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_sslot);
-    cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out);
-    cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats);
+    cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits);
+    cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out); cudaFree(c->d_state);
+    cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats); cudaFreeHost(c->h_snap);
+    if (c->wg.exec) cudaGraphExecDestroy(c->wg.exec);
+    if (c->wg.graph) cudaGraphDestroy(c->wg.graph);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     free(c);
@@ -253,14 +421,31 @@ extern "C" int ndt_b200_set_options(ndt_b200_ctx *c, uint32_t options)
     return 0;
 }
 
+extern "C" int ndt_b200_set_pool(ndt_b200_ctx *c, double bounce_factor, int slack_records, int rays_per_batch)
+{
+    if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
+    if (!(bounce_factor >= 0.0) || slack_records < 0 || rays_per_batch < 0)
+        return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_set_pool: negative argument");
+    c->bounce_factor = bounce_factor > 0.0 ? bounce_factor : 6.0;
+    c->pool_slack = slack_records;
+    c->gen_cap_max = rays_per_batch > 0 ? ((rays_per_batch + 31) & ~31) : (1 << 23);
+    return 0;
+}
+
 extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
 {
     if (!c || !fs) return ndt_set_error(NDT_B200_E_ARG, "ndt_b200_upload: NULL argument");
     const ndt_flat_header *h = &fs->h;
     int r = ndt_b200_flat_validate(fs, (size_t)h->total_bytes);
     if (r) return r;
+    /* every reject check comes before the context is touched: a failed upload leaves NO scene behind
+     * (a later launch then fails with NDT_B200_E_STATE instead of rendering a half-replaced one) */
+    c->have_scene = 0;
     if (h->npad < 4 || h->npad > 12 || !ndt_np_ops(h->npad))
         return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d dimensions: kernels are instantiated for 3..12", h->n);
+    if (h->n_lights > 256) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d lights (limit 256)", h->n_lights);
+    if (h->tree_depth + 2 > KD_STACK)
+        return ndt_set_error(NDT_B200_E_UNSUPPORTED, "kd-tree depth %d exceeds the traversal stack (%d)", h->tree_depth, KD_STACK);
     CK(cudaSetDevice(c->device));
     if (c->blob_cap < h->total_bytes) {
         CK(cudaStreamSynchronize(c->stream));
@@ -316,13 +501,10 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
             if (!(ext < 2e4)) s.any_boxed = 0;
         }
     }
-    if (h->n_lights > 256) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "%d lights (limit 256)", h->n_lights);
     {
         const ndt_flat_light *hl = (const ndt_flat_light *)((const char *)fs + h->off_lights);
         for (int i = 0; i < h->n_lights; ++i) c->light_type[i] = hl[i].type;
     }
-    if (h->tree_depth + 2 > KD_STACK)
-        return ndt_set_error(NDT_B200_E_UNSUPPORTED, "kd-tree depth %d exceeds the traversal stack (%d)", h->tree_depth, KD_STACK);
     /* the leaf-ordered record stream the warps stage through shared memory (warp.cuh) */
     {
         const size_t recb = (size_t)h->npad * 8 + 48;       /* sizeof(LeafRec<npad>), warp.cuh */
@@ -343,32 +525,45 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     return 0;
 }
 
+/* grow a pool; running out of device memory is reported like an exhausted pool (NDT_B200_E_OVERFLOW), so
+ * that the callers that can split their tile do so instead of failing */
+static int grow_pool(ndt_b200_ctx *c, void **p, size_t *cap, size_t want_bytes)
+{
+    if (*cap >= want_bytes) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(*p); *p = NULL; *cap = 0;
+    cudaError_t e = cudaMalloc(p, want_bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return ndt_set_error(NDT_B200_E_OVERFLOW, "no device memory for a %zu-byte pool; render a smaller tile", want_bytes);
+    }
+    if (e != cudaSuccess) return ndt_set_error(NDT_B200_E_CUDA, "cudaMalloc(%zu): %s", want_bytes, cudaGetErrorString(e));
+    *cap = want_bytes;
+    return 0;
+}
+
+/* logical capacity of the record pool for a pass of n0 primary slots */
+static size_t pool_records(const ndt_b200_ctx *c, int n0)
+{
+    size_t want = (size_t)n0 + (size_t)((double)n0 * c->bounce_factor) + (size_t)c->pool_slack;
+    if (want > 0x7ffffff0u) want = 0x7ffffff0u;
+    return want;
+}
+
 static int ensure_pools(ndt_b200_ctx *c, int n0, int np, int grid_threads)
 {
-    size_t want = (size_t)n0 + (size_t)((double)n0 * c->bounce_factor) + 65536;
-    if (want > 0x7ffffff0u) want = 0x7ffffff0u;
-    if (c->rec_cap < want) {
-        CK(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_rec); c->d_rec = NULL; c->rec_cap = 0;
-        CK(cudaMalloc(&c->d_rec, want * sizeof(RayRec)));
-        c->rec_cap = want;
+    int r;
+    size_t cap = c->rec_cap;             /* in records */
+    const size_t want = pool_records(c, n0);
+    {
+        size_t bytes = cap * sizeof(RayRec);
+        if ((r = grow_pool(c, (void **)&c->d_rec, &bytes, want * sizeof(RayRec)))) { c->rec_cap = 0; return r; }
+        c->rec_cap = bytes / sizeof(RayRec);
     }
-    size_t rb = (c->rec_cap - (size_t)n0 + 1) * rayin_bytes(np);
-    if (c->rays_bytes < rb) {
-        CK(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_rays); c->d_rays = NULL; c->rays_bytes = 0;
-        CK(cudaMalloc(&c->d_rays, rb));
-        c->rays_bytes = rb;
-    }
+    if ((r = grow_pool(c, &c->d_rays, &c->rays_bytes, (c->rec_cap - (size_t)n0 + 1) * rayin_bytes(np)))) return r;
     size_t words = ((size_t)c->hdr.n_items + 31) / 32;
     if (words == 0) words = 1;
-    size_t mb = words * (size_t)grid_threads * sizeof(uint32_t);
-    if (c->mb_bytes < mb) {
-        CK(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_mb); c->d_mb = NULL; c->mb_bytes = 0;
-        CK(cudaMalloc(&c->d_mb, mb));
-        c->mb_bytes = mb;
-    }
+    if ((r = grow_pool(c, (void **)&c->d_mb, &c->mb_bytes, words * (size_t)grid_threads * sizeof(uint32_t)))) return r;
     return 0;
 }
 
@@ -411,22 +606,109 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     c->sc.eye_override = 1;         /* depth and the hit / id buffers come from the left eye (ndt.c:637) */
     r = launch_pass(c, x0, y0, tw, th, dl, NULL, d_hit, d_obj_id, d_inv_depth, true, false);
     if (r) { c->sc.eye_override = 0; return r; }
-    const ndt_b200_stats left = c->last;
+    const ndt_b200_stats left = c->last;         /* fused path only; the wavefront's passes are summed by ndt_b200_sync */
     c->sc.eye_override = 2;
     r = launch_pass(c, x0, y0, tw, th, dr, NULL, NULL, NULL, NULL, false, true);
     c->sc.eye_override = 0;
     if (r) return r;
-    c->last.rays_bounce += left.rays_bounce;
-    c->last.launches += left.launches + 1;
-    if (left.generations > c->last.generations) c->last.generations = left.generations;
+    if (c->n_snap == 0) {
+        c->last.rays_bounce += left.rays_bounce;
+        c->last.launches += left.launches + 1;
+        if (left.generations > c->last.generations) c->last.generations = left.generations;
+    }
     k_anaglyph<<<(unsigned)((px + 255) / 256), 256, 0, c->stream>>>(dl, dr, (int)px, (double *)d_rgba_f64, (uint8_t *)d_rgba_u8);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, c->stream));
     return 0;
 }
 
+/* ---- the CUDA graph of one pass (see the header of this file) ------------------------------------ */
+static void wave_graph_drop(ndt_b200_ctx *c)
+{
+    if (c->wg.exec) cudaGraphExecDestroy(c->wg.exec);
+    if (c->wg.graph) cudaGraphDestroy(c->wg.graph);
+    memset(&c->wg, 0, sizeof c->wg);
+}
+
+static cudaError_t add_kernel(cudaGraph_t g, cudaGraphNode_t *node, cudaGraphNode_t *dep, const void *fn,
+                              int blocks, int threads, size_t smem, void **args)
+{
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.func = (void *)fn;
+    kp.gridDim = dim3((unsigned)blocks); kp.blockDim = dim3((unsigned)threads);
+    kp.sharedMemBytes = (unsigned)smem;
+    kp.kernelParams = args;
+    return cudaGraphAddKernelNode(node, g, dep, dep ? 1 : 0, &kp);
+}
+
+static int wave_graph_build(ndt_b200_ctx *c, int np, const WaveArgs &a, int n_sh, int trace_grid, int shade_grid)
+{
+    const NpOps *ops = ndt_np_ops(np);
+    WaveGraph &w = c->wg;
+    wave_graph_drop(c);
+    memcpy(&w.sc, &c->sc, sizeof w.sc); memcpy(&w.a, &a, sizeof w.a); w.np = np; w.n_sh = n_sh; w.specular = c->hdr.specular;
+    w.trace_grid = trace_grid; w.shade_grid = shade_grid;
+#define GK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        fprintf(stderr, "ndt_b200: %s: %s -- falling back to the host-side generation loop\n", #call, cudaGetErrorString(e_)); \
+        cudaGetLastError(); wave_graph_drop(c); c->use_graph = 0; return 1; } } while (0)
+    GK(cudaGraphCreate(&w.graph, 0));
+    cudaGraphConditionalHandle h1, h2;
+    GK(cudaGraphConditionalHandleCreate(&h1, w.graph, 1, cudaGraphCondAssignDefault));     /* generation 0 always runs */
+    GK(cudaGraphConditionalHandleCreate(&h2, w.graph, 0, cudaGraphCondAssignDefault));
+    /* loop 1: the generations */
+    cudaGraphNodeParams p1 = { cudaGraphNodeTypeConditional };
+    p1.type = cudaGraphNodeTypeConditional;
+    p1.conditional.handle = h1; p1.conditional.type = cudaGraphCondTypeWhile; p1.conditional.size = 1;
+    cudaGraphNode_t loop1, loop2, pre, fin, n_prev, n_cur;
+    GK(cudaGraphAddNode(&loop1, w.graph, NULL, 0, &p1));
+    cudaGraph_t b1 = p1.conditional.phGraph_out[0];
+    Scene sc = c->sc;
+    WaveArgs wa = a;
+    const size_t smem = ops->trace_smem_bytes(sc.any_boxed != 0);
+    void *targs[] = { &sc, &wa };
+    GK(add_kernel(b1, &n_prev, NULL, ops->trace_fn(0), trace_grid, BLOCK, smem, targs));
+    GK(add_kernel(b1, &n_cur, &n_prev, ops->shade_fn(0), shade_grid, BLOCK, 0, targs)); n_prev = n_cur;
+    if (n_sh > 0) { GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(1), trace_grid, BLOCK, smem, targs)); n_prev = n_cur; }
+    GK(add_kernel(b1, &n_cur, &n_prev, ops->shade_fn(1), shade_grid, BLOCK, 0, targs)); n_prev = n_cur;
+    WaveState *st = c->d_state;
+    int cap = a.cap, gen_cap = a.gen_cap, use_h = 1;
+    {
+        void *args[] = { &st, &cap, &gen_cap, &h1, &use_h };
+        GK(add_kernel(b1, &n_cur, &n_prev, (const void *)k_next_gen, 1, 32, 0, args));
+    }
+    /* the fold */
+    {
+        void *args[] = { &st, &h2, &use_h };
+        GK(add_kernel(w.graph, &pre, &loop1, (const void *)k_pre_resolve, 1, 32, 0, args));
+    }
+    cudaGraphNodeParams p2 = { cudaGraphNodeTypeConditional };
+    p2.type = cudaGraphNodeTypeConditional;
+    p2.conditional.handle = h2; p2.conditional.type = cudaGraphCondTypeWhile; p2.conditional.size = 1;
+    GK(cudaGraphAddNode(&loop2, w.graph, &pre, 1, &p2));
+    cudaGraph_t b2 = p2.conditional.phGraph_out[0];
+    RayRec *rec = a.rec;
+    int specular = c->hdr.specular;
+    unsigned long long *stats = c->d_stats;
+    {
+        void *args[] = { &rec, &st, &specular };
+        GK(add_kernel(b2, &n_prev, NULL, (const void *)k_resolve_dev, c->sm_count * 4, 256, 0, args));
+        void *args2[] = { &st, &h2, &use_h };
+        GK(add_kernel(b2, &n_cur, &n_prev, (const void *)k_resolve_next, 1, 32, 0, args2));
+    }
+    {
+        void *args[] = { &rec, &st, &specular, &stats };
+        GK(add_kernel(w.graph, &fin, &loop2, (const void *)k_finish_dev, c->sm_count * 8, 256, 0, args));
+    }
+    GK(cudaGraphInstantiate(&w.exec, w.graph, 0));
+#undef GK
+    w.valid = 1;
+    return 0;
+}
+
 /* One pass over a tile of the frame, or -- d_samples != NULL -- over an explicit list of n_samples
- * pixel-space positions (their colours go to d_rgba_f64[n_samples][4]) */
+ * pixel-space positions (their colours go to d_rgba_f64[n_samples][4]).  Wavefront path: nothing here
+ * waits for the device; failures inside the pass surface in ndt_b200_sync. */
 static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                        void *d_rgba_f64, void *d_rgba_u8, void *d_hit,
                        void *d_obj_id, void *d_inv_depth, bool first, bool last,
@@ -451,81 +733,125 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
     if (r) return r;
     const uint32_t mb_words = (uint32_t)((h.n_items + 31) / 32) ? (uint32_t)((h.n_items + 31) / 32) : 1u;
     uint32_t mb_shift = 0; while ((mb_words >> mb_shift) >= 64) ++mb_shift;
-
     cudaStream_t st = c->stream;
-    c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0; c->h_ctr[4] = 0; c->h_ctr[5] = 0;
-    CK(cudaMemcpyAsync(c->d_ctr, c->h_ctr, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (first) {
-        CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
-        CK(cudaEventRecord(c->ev0, st));
-    }
-
-    /* generation starts, for the backward fold */
-    int gstart[1024], gcount[1024], ngen = 0;
-    int start = 0, count = n0;
-    uint64_t launches = 0;
     const NpOps *ops = ndt_np_ops(np);
 
     if (wave) {
         /* lights that can ask for a shadow query */
         int n_sh = 0;
         for (int i = 0; i < h.n_lights; ++i) n_sh += c->light_type[i] != NDT_L_AMBIENT;
-        if ((r = grow(c, (void **)&c->d_hits, &c->hits_cap, c->rec_cap * sizeof(HitRec)))) return r;
+        /* rays per batch: a whole generation (a ray has at most two children, and only generation 1 of a
+         * frame of glass comes near 2 n0) unless that exceeds the cap */
+        int gen_cap = n0 > (1 << 29) ? (1 << 30) : ((2 * n0 + 127) & ~127);
+        if (gen_cap < 32768) gen_cap = 32768;
+        if (gen_cap > c->gen_cap_max) gen_cap = c->gen_cap_max & ~31;
+        if (gen_cap < 32) gen_cap = 32;
+        const size_t cap = pool_records(c, n0);
+        size_t bytes = c->hits_cap * sizeof(HitRec);
+        if ((r = grow_pool(c, (void **)&c->d_hits, &bytes, c->rec_cap * sizeof(HitRec)))) { c->hits_cap = 0; return r; }
+        c->hits_cap = bytes / sizeof(HitRec);
+        /* every ray of a batch may ask one shadow query per non-ambient light; answers are indexed [ray * n_lights + light] */
+        const size_t scap = (size_t)gen_cap * (size_t)(n_sh > 0 ? n_sh : 1);
+        const size_t nans = (size_t)gen_cap * (size_t)(h.n_lights > 0 ? h.n_lights : 1);
+        if (scap > 0x7ffffff0u || nans > 0x7ffffff0u)
+            return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow queue too large; render a smaller tile");
+        if ((r = grow_pool(c, (void **)&c->d_srays, &c->srays_bytes, scap * rayin_bytes(np)))) return r;
+        bytes = c->shits_cap * sizeof(HitRec);
+        if ((r = grow_pool(c, (void **)&c->d_shits, &bytes, nans * sizeof(HitRec)))) { c->shits_cap = 0; return r; }
+        c->shits_cap = bytes / sizeof(HitRec);
+
         WaveArgs a;
         memset(&a, 0, sizeof a);
-        a.n0 = n0; a.cap = (int)c->rec_cap;
-        a.x0 = x0; a.y0 = y0; a.tw = tw; a.th = th; a.bpr = bpr;
+        a.cap = (int)cap; a.gen_cap = gen_cap; a.scap = (int)scap;
         a.rec = c->d_rec; a.rays = c->d_rays; a.hits = c->d_hits;
-        a.ctr = c->d_ctr; a.stats = c->d_stats;
-        a.out_hit = (uint8_t *)d_hit; a.out_id = (int32_t *)d_obj_id; a.out_depth = (double *)d_inv_depth;
+        a.srays = c->d_srays; a.shits = c->d_shits;
+        a.st = c->d_state; a.stats = c->d_stats;
         a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
         a.mb_words = mb_words; a.mb_shift = mb_shift;
         a.leafrec = c->d_leafrec;
         a.boxrec = c->d_boxrec;
-        a.samples_xy = d_samples;
-        while (count > 0) {
-            if (ngen >= 1024) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than 1024 bounce generations");
-            gstart[ngen] = start; gcount[ngen] = count;
-            /* every ray of the generation may ask one shadow query per non-ambient light */
-            const size_t scap = (size_t)count * (size_t)(n_sh > 0 ? n_sh : 1);
-            if (scap > 0x7ffffff0u) return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow queue too large; render a smaller tile");
-            if ((r = grow(c, (void **)&c->d_srays, &c->srays_bytes, scap * rayin_bytes(np)))) return r;
-            /* answers are indexed [ray * n_lights + light] (gen.cuh) */
-            const size_t nans = (size_t)count * (size_t)(h.n_lights > 0 ? h.n_lights : 1);
-            if (nans > 0x7ffffff0u) return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow answers too large; render a smaller tile");
-            if ((r = grow(c, (void **)&c->d_shits, &c->shits_cap, nans * sizeof(HitRec)))) return r;
-            a.srays = c->d_srays; a.shits = c->d_shits; a.sslot = c->d_sslot; a.scap = (int)scap;
-            a.gen = ngen; a.start = start; a.count = count;
-            if (ngen > 0) {      /* work counters and the shadow tail start from zero */
-                CK(cudaMemsetAsync(c->d_ctr + 1, 0, sizeof(int), st));
-                CK(cudaMemsetAsync(c->d_ctr + 4, 0, 2 * sizeof(int), st));
+        const int shade_grid = ops->shade_grid(c->sm_count, gen_cap);
+
+        WaveBegin wb;
+        memset(&wb, 0, sizeof wb);
+        wb.n0 = n0; wb.x0 = x0; wb.y0 = y0; wb.tw = tw; wb.th = th; wb.bpr = bpr;
+        wb.eye = c->sc.eye_override; wb.first = first ? 1 : 0;
+        wb.samples_xy = d_samples;
+        wb.out_hit = (uint8_t *)d_hit; wb.out_id = (int32_t *)d_obj_id; wb.out_depth = (double *)d_inv_depth;
+        wb.out_f64 = (double *)d_rgba_f64; wb.out_u8 = (uint8_t *)d_rgba_u8;
+        if (first) c->n_snap = 0;
+        if (c->n_snap >= 2) return ndt_set_error(NDT_B200_E_STATE, "more than two passes pending");
+        k_begin<<<1, 32, 0, st>>>(c->d_state, wb, gen_cap, c->d_stats);
+        if (first) CK(cudaEventRecord(c->ev0, st));
+
+        bool graphed = false;
+        if (c->use_graph) {
+            WaveGraph &w = c->wg;
+            Scene key_sc;
+            memcpy(&key_sc, &c->sc, sizeof key_sc);
+            key_sc.eye_override = 0;        /* travels in WaveState */
+            const bool same = w.valid && w.np == np && w.n_sh == n_sh && w.specular == h.specular &&
+                              w.trace_grid == full_grid && w.shade_grid == shade_grid &&
+                              memcmp(&w.a, &a, sizeof a) == 0 && memcmp(&w.sc, &key_sc, sizeof key_sc) == 0;
+            if (!same) {
+                CK(cudaStreamSynchronize(st));       /* the old exec may still be running */
+                const int eo = c->sc.eye_override;
+                c->sc.eye_override = 0;
+                const int br = wave_graph_build(c, np, a, n_sh, full_grid, shade_grid);
+                c->sc.eye_override = eo;
+                if (br < 0) return br;
             }
-            int tblocks = (count + BLOCK - 1) / BLOCK;
-            if (tblocks > full_grid) tblocks = full_grid;
-            const int sblocks = (count + BLOCK - 1) / BLOCK;
-            ops->trace(0, tblocks, st, c->sc, a);
-            ops->shade(0, sblocks, st, c->sc, a);
-            launches += 2;
-            if (n_sh > 0) {
-                /* the number of queries is only known on the device: a full persistent grid reads it there */
-                size_t want_blocks = (scap + BLOCK - 1) / BLOCK;
-                ops->trace(1, want_blocks < (size_t)full_grid ? (int)want_blocks : full_grid, st, c->sc, a);
-                ++launches;
+            if (c->wg.valid) {
+                CK(cudaGraphLaunch(c->wg.exec, st));
+                graphed = true;
             }
-            ops->shade(1, sblocks, st, c->sc, a);
-            ++launches;
-            CK(cudaGetLastError());
-            ++ngen;
-            CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (c->h_ctr[3] == 2) return ndt_set_error(NDT_B200_E_CUDA, "leaf staging copy timed out (mbarrier never completed)");
-            if (c->h_ctr[3]) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
-            if (c->h_ctr[2]) return ndt_set_error(NDT_B200_E_OVERFLOW, "ray pool exhausted (%zu records); render a smaller tile", c->rec_cap);
-            int tail = c->h_ctr[0];
-            start += count;
-            count = tail - start;
         }
-    } else {
+        if (!graphed) {
+            /* the same kernels from a host loop: one read-back of `cont` per batch */
+            WaveState *hs = (WaveState *)(c->h_snap + (size_t)c->n_snap * WAVE_HEAD_BYTES);
+            cudaGraphConditionalHandle nohandle = 0;
+            int guard = 0;
+            do {
+                ops->trace(0, full_grid, st, c->sc, a);
+                ops->shade(0, shade_grid, st, c->sc, a);
+                if (n_sh > 0) ops->trace(1, full_grid, st, c->sc, a);
+                ops->shade(1, shade_grid, st, c->sc, a);
+                k_next_gen<<<1, 32, 0, st>>>(c->d_state, a.cap, a.gen_cap, nohandle, 0);
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(hs, c->d_state, WAVE_HEAD_BYTES, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            } while (hs->cont && ++guard < (1 << 20));
+            k_pre_resolve<<<1, 32, 0, st>>>(c->d_state, nohandle, 0);
+            const int ngen = hs->fail ? 0 : hs->ngen;
+            for (int g = ngen - 1; g >= 1; --g) {
+                k_resolve_dev<<<c->sm_count * 4, 256, 0, st>>>(c->d_rec, c->d_state, h.specular);
+                k_resolve_next<<<1, 32, 0, st>>>(c->d_state, nohandle, 0);
+            }
+            k_finish_dev<<<c->sm_count * 8, 256, 0, st>>>(c->d_rec, c->d_state, h.specular, c->d_stats);
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(c->h_snap + (size_t)c->n_snap * WAVE_HEAD_BYTES, c->d_state, WAVE_HEAD_BYTES,
+                           cudaMemcpyDeviceToHost, st));
+        ++c->n_snap;
+        c->n_sh_pending = n_sh;
+        if (last) {
+            CK(cudaEventRecord(c->ev1, st));
+            CK(cudaMemcpyAsync(c->h_stats, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        }
+        return 0;
+    }
+
+    /* the fused kernel (one launch per generation, host loop): A/B measurements and the counting build */
+    c->n_snap = 0;
+    c->h_ctr[0] = n0; c->h_ctr[1] = 0; c->h_ctr[2] = 0; c->h_ctr[3] = 0; c->h_ctr[4] = 0; c->h_ctr[5] = 0;
+    CK(cudaMemcpyAsync(c->d_ctr, c->h_ctr, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (first) {
+        CK(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), st));
+        CK(cudaEventRecord(c->ev0, st));
+    }
+    int gstart[1024], gcount[1024], ngen = 0;
+    int start = 0, count = n0;
+    uint64_t launches = 0;
     GenArgs a;
     memset(&a, 0, sizeof a);
     a.n0 = n0; a.cap = (int)c->rec_cap;
@@ -557,7 +883,6 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
         start += count;
         count = tail - start;
     }
-    }
     for (int g = ngen - 1; g >= 1; --g) {
         k_resolve<<<(gcount[g] + 255) / 256, 256, 0, st>>>(c->d_rec, gstart[g], gcount[g], h.specular);
         ++launches;
@@ -584,6 +909,28 @@ extern "C" int ndt_b200_sync(ndt_b200_ctx *c)
     if (!c) return ndt_set_error(NDT_B200_E_ARG, "NULL ctx");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->n_snap > 0) {
+        /* the wavefront: what the device-side loop did, pass by pass */
+        const int passes = c->n_snap;
+        c->n_snap = 0;
+        memset(&c->last, 0, sizeof c->last);
+        for (int p = 0; p < passes; ++p) {
+            const WaveState *hs = (const WaveState *)(c->h_snap + (size_t)p * WAVE_HEAD_BYTES);
+            const int pool = hs->fail & 0xff, kd = hs->fail >> 8;
+            if (kd == 2) return ndt_set_error(NDT_B200_E_CUDA, "leaf staging copy timed out (mbarrier never completed)");
+            if (kd) return ndt_set_error(NDT_B200_E_OVERFLOW, "kd traversal stack overflow");
+            if (pool == 3) return ndt_set_error(NDT_B200_E_OVERFLOW, "more than %d bounce generations", WAVE_MAX_GEN);
+            if (pool == 2) return ndt_set_error(NDT_B200_E_OVERFLOW, "shadow queue exhausted; render a smaller tile");
+            if (pool) return ndt_set_error(NDT_B200_E_OVERFLOW, "ray pool exhausted; render a smaller tile");
+            if (hs->cont) return ndt_set_error(NDT_B200_E_CUDA, "the generation loop did not finish");
+            c->last.rays_bounce += (uint64_t)(hs->tail - hs->n0);
+            if ((uint32_t)hs->ngen > c->last.generations) c->last.generations = (uint32_t)hs->ngen;
+            /* k_begin, 4 or 5 kernels per batch, k_pre_resolve, 2 per folded generation, k_finish */
+            c->last.launches += 1 + (uint64_t)hs->iters * (c->n_sh_pending > 0 ? 5 : 4) + 1 +
+                                2 * (uint64_t)(hs->ngen > 1 ? hs->ngen - 1 : 0) + 1;
+        }
+        if (passes == 2) c->last.launches += 1;      /* k_anaglyph */
+    }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last.device_ms = ms;
     c->last.rays_primary = c->h_stats[5];     /* pixels that were traced (all but HIDEF_3D's blanking rows), per eye */
@@ -612,28 +959,38 @@ static void stats_add(ndt_b200_stats *acc, const ndt_b200_stats *s)
     acc->device_ms += s->device_ms;
 }
 
+/* One tile into HOST buffers.  A tile whose ray trees do not fit the record pool (or whose pools do not fit
+ * the device) is rendered as two half-height tiles; a single row that still overflows gets a larger pool for
+ * that one retry.  bounce_factor itself is never left changed. */
 static int render_rows(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                        double *f64, uint8_t *u8, uint8_t *hit, int32_t *id, double *dep,
                        ndt_b200_stats *acc, int depth)
 {
     const size_t px = (size_t)tw * th;
     const size_t need = px * (32 + 4 + 1 + 4 + 8) + 256;
-    if (c->out_cap < need) {
-        CK(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_out); c->d_out = NULL; c->out_cap = 0;
-        CK(cudaMalloc(&c->d_out, need));
-        c->out_cap = need;
-    }
-    char *b = c->d_out;
-    double *d_f64 = (double *)b;              b += px * 32;
-    double *d_dep = (double *)b;              b += px * 8;
-    int32_t *d_id = (int32_t *)b;             b += px * 4;
-    uint8_t *d_u8 = (uint8_t *)b;             b += px * 4;
-    uint8_t *d_hit = (uint8_t *)b;
-    int r = ndt_b200_launch_tile(c, x0, y0, tw, th, f64 ? d_f64 : NULL, u8 ? d_u8 : NULL,
+    int r = grow_pool(c, (void **)&c->d_out, &c->out_cap, need);
+    if (!r) {
+        char *b = c->d_out;
+        double *d_f64 = (double *)b;              b += px * 32;
+        double *d_dep = (double *)b;              b += px * 8;
+        int32_t *d_id = (int32_t *)b;             b += px * 4;
+        uint8_t *d_u8 = (uint8_t *)b;             b += px * 4;
+        uint8_t *d_hit = (uint8_t *)b;
+        r = ndt_b200_launch_tile(c, x0, y0, tw, th, f64 ? d_f64 : NULL, u8 ? d_u8 : NULL,
                                  hit ? d_hit : NULL, id ? d_id : NULL, dep ? d_dep : NULL);
-    if (r == NDT_B200_E_OVERFLOW && depth < 12) {
+        if (!r) {
+            cudaStream_t st = c->stream;
+            if (f64) CK(cudaMemcpyAsync(f64, d_f64, px * 32, cudaMemcpyDeviceToHost, st));
+            if (u8)  CK(cudaMemcpyAsync(u8, d_u8, px * 4, cudaMemcpyDeviceToHost, st));
+            if (hit) CK(cudaMemcpyAsync(hit, d_hit, px, cudaMemcpyDeviceToHost, st));
+            if (id)  CK(cudaMemcpyAsync(id, d_id, px * 4, cudaMemcpyDeviceToHost, st));
+            if (dep) CK(cudaMemcpyAsync(dep, d_dep, px * 8, cudaMemcpyDeviceToHost, st));
+            r = ndt_b200_sync(c);           /* the device-side loop reports an exhausted pool here */
+        }
+    }
+    if (r == NDT_B200_E_OVERFLOW && depth < 16) {
         cudaStreamSynchronize(c->stream);
+        c->n_snap = 0;
         if (th >= 2) {       /* rows are contiguous in a tile-row-major buffer: split along y */
             int h1 = th / 2;
             size_t o1 = (size_t)tw * h1;
@@ -642,17 +999,17 @@ static int render_rows(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
             return render_rows(c, x0, y0 + h1, tw, th - h1, f64 ? f64 + 4 * o1 : NULL, u8 ? u8 + 4 * o1 : NULL,
                                hit ? hit + o1 : NULL, id ? id + o1 : NULL, dep ? dep + o1 : NULL, acc, depth + 1);
         }
-        c->bounce_factor *= 4.0;
-        return render_rows(c, x0, y0, tw, th, f64, u8, hit, id, dep, acc, depth + 1);
+        if (c->bounce_factor < 1e5) {
+            const double keep = c->bounce_factor;
+            const int keep_slack = c->pool_slack;
+            c->bounce_factor = keep * 4.0 + 4.0;
+            if (c->pool_slack < 4096) c->pool_slack = 4096;
+            r = render_rows(c, x0, y0, tw, th, f64, u8, hit, id, dep, acc, depth + 1);
+            c->bounce_factor = keep;
+            c->pool_slack = keep_slack;
+            return r;
+        }
     }
-    if (r) return r;
-    cudaStream_t st = c->stream;
-    if (f64) CK(cudaMemcpyAsync(f64, d_f64, px * 32, cudaMemcpyDeviceToHost, st));
-    if (u8)  CK(cudaMemcpyAsync(u8, d_u8, px * 4, cudaMemcpyDeviceToHost, st));
-    if (hit) CK(cudaMemcpyAsync(hit, d_hit, px, cudaMemcpyDeviceToHost, st));
-    if (id)  CK(cudaMemcpyAsync(id, d_id, px * 4, cudaMemcpyDeviceToHost, st));
-    if (dep) CK(cudaMemcpyAsync(dep, d_dep, px * 8, cudaMemcpyDeviceToHost, st));
-    r = ndt_b200_sync(c);
     if (r) return r;
     stats_add(acc, &c->last);
     return 0;
@@ -940,13 +1297,22 @@ static int aa_render_samples(ndt_b200_ctx *c, const double *d_xy, int n, double 
     if (!r) r = ndt_b200_sync(c);
     if (r == NDT_B200_E_OVERFLOW && depth < 24) {
         cudaStreamSynchronize(c->stream);
+        c->n_snap = 0;
         if (n >= 64) {
             const int h1 = n / 2;
             if ((r = aa_render_samples(c, d_xy, h1, d_samp, acc, depth + 1))) return r;
             return aa_render_samples(c, d_xy + 2 * (size_t)h1, n - h1, d_samp + 4 * (size_t)h1, acc, depth + 1);
         }
-        c->bounce_factor *= 4.0;
-        return aa_render_samples(c, d_xy, n, d_samp, acc, depth + 1);
+        if (c->bounce_factor < 1e5) {
+            const double keep = c->bounce_factor;
+            const int keep_slack = c->pool_slack;
+            c->bounce_factor = keep * 4.0 + 4.0;
+            if (c->pool_slack < 4096) c->pool_slack = 4096;
+            r = aa_render_samples(c, d_xy, n, d_samp, acc, depth + 1);
+            c->bounce_factor = keep;
+            c->pool_slack = keep_slack;
+            return r;
+        }
     }
     if (r) return r;
     stats_add(acc, &c->last);
@@ -987,12 +1353,17 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
     AA_CK(cudaMemsetAsync(d_res, 0, sizeof(unsigned long long), st));
 
     /* the initial image: one sample per corner (render_lines_thread with width+1, height+1) */
-    for (int attempt = 0; ; ++attempt) {
-        r = ndt_b200_launch_tile(c, 0, 0, W + 1, H + 1, d_img, NULL, NULL, NULL, NULL);
-        if (!r) r = ndt_b200_sync(c);
-        if (r != NDT_B200_E_OVERFLOW || attempt >= 6) break;
-        cudaStreamSynchronize(st);
-        c->bounce_factor *= 2.0;        /* deep ray trees (glass, mirrors): a larger record pool */
+    {
+        const double keep = c->bounce_factor;
+        for (int attempt = 0; ; ++attempt) {
+            r = ndt_b200_launch_tile(c, 0, 0, W + 1, H + 1, d_img, NULL, NULL, NULL, NULL);
+            if (!r) r = ndt_b200_sync(c);
+            if (r != NDT_B200_E_OVERFLOW || attempt >= 6) break;
+            cudaStreamSynchronize(st);
+            c->n_snap = 0;
+            c->bounce_factor *= 2.0;        /* deep ray trees (glass, mirrors): a larger record pool for this frame */
+        }
+        c->bounce_factor = keep;
     }
     if (r) goto aa_done;
     stats_add(&acc, &c->last);

@@ -54,6 +54,22 @@ void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveAr
     else k_shade<NP, 0><<<blocks, BLOCK, 0, st>>>(sc, a);
 }
 
+const void *trace_fn(int mode) { return mode ? (const void *)k_trace<NP, 1> : (const void *)k_trace<NP, 0>; }
+const void *shade_fn(int phase) { return phase ? (const void *)k_shade<NP, 1> : (const void *)k_shade<NP, 0>; }
+int shade_grid(int sm_count, int gen_cap)
+{
+#if NDT_SHADE_LOOP
+    int b0 = 0, b1 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_shade<NP, 0>, BLOCK, 0) != cudaSuccess || b0 < 1) b0 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_shade<NP, 1>, BLOCK, 0) != cudaSuccess || b1 < 1) b1 = 1;
+    (void)gen_cap;
+    return (b0 > b1 ? b0 : b1) * sm_count * 2;
+#else
+    (void)sm_count;
+    return (gen_cap + BLOCK - 1) / BLOCK;
+#endif
+}
+
 void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out)
 {
     k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out, (BoxRec<NP> *)box_out);
@@ -71,4 +87,5 @@ void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const 
 }
 }  // namespace
 
-extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { trace_blocks_per_sm, trace, shade, blocks_per_sm, generation, pack_leaf, trace_rays };
+extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { trace_blocks_per_sm, trace, shade, blocks_per_sm, generation, pack_leaf, trace_rays,
+                                                     trace_fn, shade_fn, trace_smem, shade_grid };

@@ -176,16 +176,128 @@ def test_error_behaviour():
 
 
 def test_small_ray_pool_splits_the_tile(oracle_lib):
-    """pool exhaustion is recovered by halving the tile, not by dropping rays"""
-    import ctypes as C
+    """Pool exhaustion is recovered by halving the tile (render_rows), and a single row that still does not fit
+    by one retry with a larger pool -- never by dropping rays.  ndt_b200_set_pool shrinks the record pool to
+    10 % headroom and no slack, so the 160x90 frame of config 1 (1.5 bounce rays per pixel) overflows at every
+    level of the split down to single rows."""
     flat = load_flat("config1_default4d")
+    want = oracle_render(oracle_lib, flat)
     c = ndt_b200.Context(0)
     try:
         c.upload(flat)
-        full = c.render_tile(0, 0, flat.header.width, flat.header.height)
-        want = oracle_render(oracle_lib, flat)
-        assert np.array_equal(full.obj_id, want.id)
-        assert full.stats.rays_bounce == want.stats["rays_bounce"] or \
-            abs(full.stats.rays_bounce - want.stats["rays_bounce"]) < 0.002 * want.stats["rays_bounce"]
+        ref = c.render_tile(0, 0, flat.header.width, flat.header.height)
+        c.set_pool(bounce_factor=0.1, slack_records=0)
+        # the async entry point reports the exhausted pool at sync time and does not retry
+        import torch
+        u8 = torch.zeros((flat.header.height, flat.header.width, 4), dtype=torch.uint8, device="cuda:0")
+        c.launch_tile(0, 0, flat.header.width, flat.header.height, d_u8=u8.data_ptr())
+        with pytest.raises(ndt_b200.NdtB200Error) as e:
+            c.sync()
+        assert e.value.code == -5                       # NDT_B200_E_OVERFLOW
+        got = c.render_tile(0, 0, flat.header.width, flat.header.height)
+        assert got.stats.launches > 8 * ref.stats.launches, "the tile was not split"
+        assert bits_equal(got.rgba_f64, ref.rgba_f64) and bits_equal(got.rgba_u8, ref.rgba_u8)
+        assert np.array_equal(got.hit, want.hit) and np.array_equal(got.obj_id, want.id)
+        assert bits_equal(got.inv_depth, want.depth)
+        assert got.stats.rays_unique == ref.stats.rays_unique
+        # the pool sizing is back to what was set, not left inflated by the single-row retries
+        c.set_pool()                                    # defaults
+        again = c.render_tile(0, 0, flat.header.width, flat.header.height)
+        assert again.stats.launches == ref.stats.launches
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("key", ["config1_default4d", "config5_mixed10d", "view_anaglyph5d"])
+def test_generations_in_batches_give_the_same_frame(key):
+    """A generation larger than rays_per_batch is worked off in several iterations of the device-side loop
+    (k_next_gen): same pixels, same ray counts, more launches."""
+    flat = load_flat(key)
+    w, h = flat.header.width, flat.header.height
+    c = ndt_b200.Context(0)
+    try:
+        c.upload(flat)
+        ref = c.render_tile(0, 0, w, h)
+        c.set_pool(rays_per_batch=1024)
+        got = c.render_tile(0, 0, w, h)
+        assert got.stats.launches > ref.stats.launches
+        assert bits_equal(got.rgba_f64, ref.rgba_f64) and bits_equal(got.rgba_u8, ref.rgba_u8)
+        assert np.array_equal(got.obj_id, ref.obj_id) and np.array_equal(got.hit, ref.hit)
+        assert got.stats.rays_unique == ref.stats.rays_unique and got.stats.generations == ref.stats.generations
+    finally:
+        c.close()
+
+
+def test_graph_and_host_loop_agree(monkeypatch):
+    """The CUDA graph with its WHILE nodes and the host loop over the same kernels (NDT_B200_NO_GRAPH=1) are
+    the same render; the fused kernel (OPT_FUSED) still gives the same pixels too."""
+    flat = load_flat("config1_default4d")
+    w, h = flat.header.width, flat.header.height
+    a = ndt_b200.Context(0)
+    monkeypatch.setenv("NDT_B200_NO_GRAPH", "1")
+    b = ndt_b200.Context(0)
+    monkeypatch.delenv("NDT_B200_NO_GRAPH")
+    try:
+        a.upload(flat); b.upload(flat)
+        fa = a.render_tile(0, 0, w, h)
+        fb = b.render_tile(0, 0, w, h)
+        assert bits_equal(fa.rgba_f64, fb.rgba_f64) and np.array_equal(fa.obj_id, fb.obj_id)
+        assert fa.stats.as_dict().keys() == fb.stats.as_dict().keys()
+        for k in ("rays_primary", "rays_bounce", "rays_shadow", "rays_ref", "samples", "generations", "launches"):
+            assert getattr(fa.stats, k) == getattr(fb.stats, k), k
+        a.set_options(ndt_b200.OPT_FUSED)
+        fc = a.render_tile(0, 0, w, h)
+        a.set_options(0)
+        assert bits_equal(fa.rgba_f64, fc.rgba_f64)
+        assert fc.stats.rays_unique == fa.stats.rays_unique
+    finally:
+        a.close(); b.close()
+
+
+# BASELINE.json configs at the sizes bench.py times them at (VERDICT r1, missing #1): the culls of k_trace depend on
+# how tight an 8x4-pixel bundle is, i.e. on the resolution, so parity at 96x54 says nothing about 1920x1080.
+FULL_SIZE = [("config2_hypercube8d", 1920, 1080), ("config4_balls5d", 3840, 2160), ("config5_yaml10d", 1920, 1080)]
+
+
+def pick_tiles(hit, oid, t=64):
+    """sample tiles of a frame, chosen from its own hit / id buffers: the tile with the most distinct objects
+    (silhouettes, overlapping faces), a tile that is half hit and half miss, one without any hit (sky), one
+    fully covered by a single object (floor), and the four corners"""
+    H, W = hit.shape
+    best = {}
+    for y0 in range(0, H - t + 1, t):
+        for x0 in range(0, W - t + 1, t):
+            h = hit[y0:y0 + t, x0:x0 + t]
+            ids = oid[y0:y0 + t, x0:x0 + t]
+            nd = len(np.unique(ids))
+            frac = float(h.mean())
+            cand = {"objects": nd, "edge": -abs(frac - 0.5), "sky": 1.0 if frac == 0.0 else -1.0,
+                    "floor": 1.0 if (frac == 1.0 and nd == 1) else -1.0}
+            for k, v in cand.items():
+                if k not in best or v > best[k][0]:
+                    best[k] = (v, x0, y0)
+    tiles = [(x0, y0) for k, (v, x0, y0) in best.items() if not (k in ("sky", "floor") and v < 0)]
+    tiles += [(0, 0), (W - t, 0), (0, H - t), (W - t, H - t)]
+    return sorted(set(tiles))
+
+
+@pytest.mark.parametrize("key,w,h", FULL_SIZE, ids=[k for k, _, _ in FULL_SIZE])
+def test_benchmarked_sizes_against_oracle_tiles(key, w, h, ctx, oracle_lib):
+    flat = load_flat(key).retarget(w, h)
+    ctx.upload(flat)
+    got = ctx.render_tile(0, 0, w, h, want=("u8", "hit", "id", "depth"))
+    assert got.stats.rays_primary == w * h
+    assert (got.obj_id[got.hit == 1] >= 0).all() and got.obj_id.max() < flat.header.n_items
+    tiles = pick_tiles(got.hit, got.obj_id)
+    assert len(tiles) >= 5
+    worst = 1.0
+    for (x0, y0) in tiles:
+        want = oracle_render(oracle_lib, flat, x0=x0, y0=y0, tw=64, th=64)
+        sl = (slice(y0, y0 + 64), slice(x0, x0 + 64))
+        assert np.array_equal(got.hit[sl], want.hit), (key, x0, y0, int((got.hit[sl] != want.hit).sum()))
+        assert np.array_equal(got.obj_id[sl], want.id), (key, x0, y0, int((got.obj_id[sl] != want.id).sum()))
+        assert bits_equal(got.inv_depth[sl], want.depth), (key, x0, y0)
+        ok, dmax, nbad, exact = colour_report(got.rgba_u8[sl], want.u8)
+        worst = min(worst, ok)
+        assert ok >= LSB_OK_FRACTION, (key, x0, y0, ok, dmax, nbad)
+    print(f"\n{key} {w}x{h}: {len(tiles)} oracle tiles of 64x64, hit/id/depth bit-exact, u8 within 1 LSB >= {worst*100:.3f}%")
