@@ -97,7 +97,8 @@ def lib():
     L.ndt_b200_destroy.restype = None
     L.ndt_b200_upload.argtypes = [C.c_void_p, C.c_void_p]
     L.ndt_b200_set_options.argtypes = [C.c_void_p, C.c_uint32]
-    L.ndt_b200_set_pool.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+    if hasattr(L, "ndt_b200_set_pool"):      # absent from round-1 builds (A/B runs with NDT_B200_LIB)
+        L.ndt_b200_set_pool.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
     L.ndt_b200_render_tile.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5 + [C.POINTER(Stats)]
     L.ndt_b200_launch_tile.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 5
     L.ndt_b200_sync.argtypes = [C.c_void_p]

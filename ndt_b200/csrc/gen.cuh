@@ -328,6 +328,62 @@ __device__ __forceinline__ void hit_load(const HitRec *src, double &t, int &id, 
     t = a.x; id = __double2loint(a.y); win = __double2hiint(a.y); found = __double2loint(b.x);
 }
 
+/* ---- queue layout of the wavefront: word-major ------------------------------------------------------------
+ * A queue entry (ray, record, hit, hit geometry) is a handful of 16-byte words.  Stored entry after entry, the
+ * 32 lanes of a warp reading word c of 32 consecutive entries touch 32 different sectors 80-176 bytes apart:
+ * ncu on k_shade (profiles/r02_ncu_k_shade_aos_*): 73 % of the stall samples long_scoreboard on exactly those
+ * loads, L1 hit rate 54-61 %, 42 cycles per issued instruction.  Stored word after word -- word c of entry e at
+ * base[c * stride + e] -- the same access is 512 contiguous bytes. */
+template <int NP>
+__device__ __forceinline__ void ray_store_s(double2 *base, size_t stride, size_t e, const double *o, const double *v,
+                                            double frac, int depth, int aux = 0)
+{
+    double2 *d = base + e;
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) d[(size_t)(i / 2) * stride] = make_double2(o[i], o[i + 1]);
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) d[(size_t)(NP / 2 + i / 2) * stride] = make_double2(v[i], v[i + 1]);
+    d[(size_t)NP * stride] = make_double2(frac, __hiloint2double(aux, depth));   /* frac | depth, aux (shadow queries: where the answer goes) */
+}
+template <int NP>
+__device__ __forceinline__ void ray_load_s(const double2 *base, size_t stride, size_t e, double *o, double *v,
+                                           double &frac, int &depth, int &aux)
+{
+    const double2 *d = base + e;
+    double2 t[NP + 1];
+    NDT_UNROLL
+    for (int i = 0; i <= NP; ++i) t[i] = d[(size_t)i * stride];          /* all loads in flight before the first use */
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) { o[i] = t[i / 2].x; o[i + 1] = t[i / 2].y; }
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) { v[i] = t[NP / 2 + i / 2].x; v[i + 1] = t[NP / 2 + i / 2].y; }
+    frac = t[NP].x;
+    depth = __double2loint(t[NP].y);
+    aux = __double2hiint(t[NP].y);
+}
+__device__ __forceinline__ void rec_load_s(RayRec &r, const double2 *base, size_t stride, size_t e)
+{
+    double2 *d = reinterpret_cast<double2 *>(&r);
+    NDT_UNROLL
+    for (int i = 0; i < (int)(sizeof(RayRec) / 16); ++i) d[i] = base[(size_t)i * stride + e];
+}
+__device__ __forceinline__ void rec_store_s(double2 *base, size_t stride, size_t e, const RayRec &r)
+{
+    const double2 *s = reinterpret_cast<const double2 *>(&r);
+    NDT_UNROLL
+    for (int i = 0; i < (int)(sizeof(RayRec) / 16); ++i) base[(size_t)i * stride + e] = s[i];
+}
+__device__ __forceinline__ void hit_store_s(double2 *base, size_t stride, size_t e, double t, int id, int win, int found)
+{
+    base[e] = make_double2(t, __hiloint2double(win, id));
+    base[stride + e] = make_double2(__hiloint2double(0, found), 0.0);
+}
+__device__ __forceinline__ void hit_load_s(const double2 *base, size_t stride, size_t e, double &t, int &id, int &win, int &found)
+{
+    const double2 a = base[e], b = base[stride + e];
+    t = a.x; id = __double2loint(a.y); win = __double2hiint(a.y); found = __double2loint(b.x);
+}
+
 /* ---- the generation loop lives on the device -------------------------------------------------------
  * Everything a launch needs to know about "which rays now" is read from WaveState in device memory, so the
  * host can enqueue a whole frame without knowing how many bounce generations it has: one CUDA graph per
@@ -336,7 +392,10 @@ __device__ __forceinline__ void hit_load(const HitRec *src, double &t, int &id, 
  * for one batch).  Three groups of fields, each on its own cache lines: constant for a pass (k_begin),
  * constant for a launch (k_begin / k_next_gen), and the atomics of the running launch. */
 constexpr int WAVE_MAX_GEN = 1024;
-struct WaveState {
+/* what every kernel of the loop reads and none of them writes: copied to shared memory at the top of each
+ * kernel (wave_head_load), because read from global memory where they are used these values cost an L2 round
+ * trip per ray (the compiler hoists ordinary loads into registers instead, +40-60 registers) */
+struct WaveHead {
     /* the pass: written by k_begin */
     int n0;                  /* slots of generation 0 (tile padded to 8x4 blocks, or the sample count) */
     int x0, y0, tw, th, bpr; /* tile, and 8-pixel blocks per tile row (0: an explicit sample list) */
@@ -349,8 +408,8 @@ struct WaveState {
     double *out_depth;
     double *out_f64;
     uint8_t *out_u8;
-    /* the launch: written by k_begin and k_next_gen / k_resolve_next, read-only for every other kernel */
-    alignas(128) int gen;    /* generation of the current batch; 0: rays are generated from pixels */
+    /* the launch: written by k_begin and k_next_gen / k_resolve_next */
+    int gen;                 /* generation of the current batch; 0: rays are generated from pixels */
     int start, count;        /* the batch: record slots [start, start + count) */
     int gen_start, gen_count; /* the generation the batch belongs to */
     int ngen;                /* finished generations (gstart / gcount filled) */
@@ -358,30 +417,53 @@ struct WaveState {
     int cont;                /* the loop goes on (mirror of the WHILE node's condition, for the host loop) */
     int resolve_g;           /* the generation k_resolve folds next */
     int fail;                /* copy of pool_overflow | kd_fault << 8 when the loop ended */
-    /* atomics of the running launch */
+};
+static_assert(sizeof(WaveHead) == 120, "WaveHead is copied as 15 8-byte words");
+struct WaveState : WaveHead {
+    /* atomics of the running launch, one cache line each: every warp of the GPU hits them */
     alignas(128) int tail;   /* next free record slot */
-    int next0;               /* work counter, radiance rays */
-    int stail;               /* shadow queue tail */
-    int next1;               /* work counter, shadow queries */
-    int pool_overflow;       /* 1 record pool, 2 shadow queue, 3 more than WAVE_MAX_GEN generations */
+    alignas(128) int next0;  /* work counter, radiance rays */
+    alignas(128) int stail;  /* shadow queue tail */
+    alignas(128) int next1;  /* work counter, shadow queries */
+    alignas(128) int nextA;  /* work counters of k_shade<A> / k_shade<B> */
+    alignas(128) int nextB;
+    alignas(128) int nextL;  /* ... of k_light / k_libm */
+    alignas(128) int nextM;
+    alignas(128) int nextR;  /* ... of k_resolve_dev / k_finish_dev */
+    alignas(128) int nextF;
+    alignas(128) int pool_overflow;  /* 1 record pool, 2 shadow queue, 3 more than WAVE_MAX_GEN generations */
     int kd_fault;            /* 1 traversal stack overflow, 2 staging copy timed out */
     alignas(128) int gstart[WAVE_MAX_GEN];
     int gcount[WAVE_MAX_GEN];
 };
+/* every thread of the block calls it before anything else */
+__device__ __forceinline__ const WaveHead *wave_head_load(const WaveState *st)
+{
+    __shared__ __align__(16) unsigned long long sh_head[sizeof(WaveHead) / 8];
+    if (threadIdx.x < sizeof(WaveHead) / 8)
+        sh_head[threadIdx.x] = reinterpret_cast<const unsigned long long *>(static_cast<const WaveHead *>(st))[threadIdx.x];
+    __syncthreads();
+    return reinterpret_cast<const WaveHead *>(sh_head);
+}
 
 struct WaveArgs {            /* constant for the life of a graph: pool pointers and capacities */
     int cap;                 /* record pool capacity */
     int gen_cap;             /* rays per batch (multiple of 32) */
     int scap;                /* shadow queue capacity (gen_cap * non-ambient lights) */
     int pad;
-    RayRec *rec;
-    void *rays;              /* RayIn<NP>[cap - n0], slot s lives at rays[s - n0] */
-    HitRec *hits;            /* [cap], by slot */
-    void *srays;             /* shadow queries RayIn<NP>[scap]: frac = dist_limit, depth = 1 + light index for the
-                                any-hit query of a DIRECTIONAL light, else 0 */
-    HitRec *shits;           /* [gen_cap * n_lights]: the answer to the shadow query of (ray, light) at [ray * n_lights + light],
-                                ray counted from the start of the batch; the query carries that index (ray_aux), so
-                                k_shade<B> reads its answers without an indirection (entries without a query are never read) */
+    /* all word-major (see ray_store_s): */
+    double2 *rec;            /* RayRec, 5 words, stride cap */
+    double2 *rays;           /* RayIn<NP>, NP + 1 words, stride cap; slot s lives at entry s - n0 */
+    double2 *hits;           /* HitRec, 2 words, stride cap, by slot */
+    double2 *srays;          /* shadow queries, NP + 1 words, stride scap: frac = dist_limit, depth = 1 + light index for
+                                the any-hit query of a DIRECTIONAL light, else 0 */
+    double2 *shits;          /* [gen_cap * n_lights]: the answer to the shadow query of (ray, light) at [ray * n_lights + light],
+                                ray counted from the start of the batch; the query carries that index (ray_aux).  The slot
+                                is rewritten in place by k_light (LightGeo) and k_libm (LightTerm); entries without a
+                                query are never read */
+    double2 *hgeo;           /* NP words, stride gen_cap: hit point and normal of every shaded ray of the batch (k_shade<A>) */
+    uint32_t *qmask;         /* [mw][gen_cap]: bit 0 = shaded, bit 1 + it = light it was asked (k_shade<A>) */
+    uint32_t mw, nl_eff;     /* nl_eff = max(n_lights, 1) */
     WaveState *st;
     unsigned long long *stats; /* [0] shadow rays [1] flops [2] rays_ref [3] samples [4] hit pixels [5] traced pixels */
     uint32_t *mb_bits;
@@ -401,15 +483,9 @@ struct WaveBegin {
     uint8_t *out_u8;
 };
 
-/* WaveState fields are read where they are used: an ordinary load is hoisted to the top of the function by the
- * compiler and then lives in a register across the whole shading code (+40-60 registers measured); a volatile
- * load stays where it is written */
-template <class T> __device__ __forceinline__ T ld_here(const T *p) { return *(const volatile T *)p; }
-template <class T> __device__ __forceinline__ T *ld_here(T *const *p) { return (T *)*(T *const volatile *)p; }
-
 /* the ray of slot start + r of the current batch */
 template <int NP>
-__device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, const WaveState *st, int gen, int start, int count,
+__device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, const WaveHead *hd, int gen, int start, int count,
                                          int r, int lane, double *o, double *v, double &frac, int &depth, int &tx, int &ty)
 {
     bool active = r < count;
@@ -417,19 +493,19 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, con
     depth = sc.max_optic_depth;
     tx = ty = 0;
     if (gen == 0) {
-        const double *sxy = ld_here(&st->samples_xy);
+        const double *sxy = hd->samples_xy;
         const int s = start + r;
         if (sxy) {
             if (active) primary_ray_at<NP>(sc, sxy[2 * (size_t)s], sxy[2 * (size_t)s + 1], o, v);
         } else {
-            const int blk = s >> 5, bpr = ld_here(&st->bpr);
+            const int blk = s >> 5, bpr = hd->bpr;
             tx = (blk % bpr) * 8 + (lane & 7);
             ty = (blk / bpr) * 4 + (lane >> 3);
-            active = active && tx < ld_here(&st->tw) && ty < ld_here(&st->th);
-            if (active) active = primary_ray<NP>(sc, ld_here(&st->x0) + tx, ld_here(&st->y0) + ty, o, v, ld_here(&st->eye));
+            active = active && tx < hd->tw && ty < hd->th;
+            if (active) active = primary_ray<NP>(sc, hd->x0 + tx, hd->y0 + ty, o, v, hd->eye);
         }
     } else if (active) {
-        ray_load<NP>((const RayIn<NP> *)a.rays + (start + r - ld_here(&st->n0)), o, v, frac, depth);
+        { int aux_; ray_load_s<NP>(a.rays, (size_t)a.cap, (size_t)(start + r - hd->n0), o, v, frac, depth, aux_); }
     }
     return active;
 }
@@ -440,8 +516,9 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
 {
     const int lane = threadIdx.x & 31;
     WaveState *st = a.st;
-    const int gen = st->gen, start = st->start;
-    int count = st->count;
+    const WaveHead *hd = wave_head_load(st);
+    const int gen = hd->gen, start = hd->start;
+    int count = hd->count;
     if (MODE == 1) {             /* written by k_shade<A>, complete before this launch started */
         count = *(volatile const int *)&st->stail;
         if (count > a.scap) count = a.scap;
@@ -471,36 +548,75 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         int dest = 0;                /* MODE 1: index of the answer in shits[] */
         if (MODE == 0) {
             double frac; int depth, tx, ty;
-            want = wave_ray<NP>(sc, a, st, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+            want = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
         } else {
             want = r < count;
             if (want) {
                 int code;
-                ray_load<NP>((const RayIn<NP> *)a.srays + r, o, v, limit, code);
+                ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)r, o, v, limit, code, dest);
                 dir_light = code - 1;
-                dest = ray_aux<NP>((const RayIn<NP> *)a.srays + r);
             }
         }
         Hit T;
         trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
         if (ws.fault) break;     /* warp-uniform (warp.cuh) */
-        if (want) hit_store(MODE == 0 ? a.hits + (start + r) : a.shits + dest, T.t, T.id, T.win, T.found);
+        if (want) {
+            if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), T.t, T.id, T.win, T.found);
+            else hit_store_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, T.t, T.id, T.win, T.found);
+        }
     }
     if (kd_overflow) atomicMax(&st->kd_fault, 1);
     if (ws.fault) atomicMax(&st->kd_fault, 2);
 }
 
-/* PHASE 0 = A (emit the shadow queries), PHASE 1 = B (consume the answers, finish the ray): one ray of the
- * batch per thread. */
+/* ---- shading: four kernels around the shadow trace ------------------------------------------------------
+ *   k_shade<NP,0>  (A, per ray)    hit point + normal of the winner (materialise), stored for the later phases;
+ *                                  side tests (ndt.c:149-169); one shadow query per light that needs one; the
+ *                                  primary ray's hit / id / depth outputs
+ *   k_light<NP>    (per query)     the vector half of the lit term (light_geom, wave.cuh): does the light see
+ *                                  the shaded point, acos argument, specular dot product -> three scalars
+ *   k_libm         (per query)     acos / cos / pow on those scalars (light_libm): no vectors, ~40 registers,
+ *                                  full occupancy -- the libm expansions were the long dependent FP64 chains
+ *                                  of the old phase B, run there at 8-12 warps per SM
+ *   k_shade<NP,1>  (B, per ray)    colour in the reference's light order from the (scale, rvn) pairs, RayRec,
+ *                                  reflection / refraction rays of the next generation
+ * All have fixed grids (CUDA graph) and draw 32 rays / queries per warp from a counter in WaveState: the cost
+ * of a ray varies from a sky pixel to a glass sphere under three lights, and a static stride left the tail of
+ * every launch to the warps that drew the expensive ones (profiles/r02_experiments.md). */
 #ifndef NDT_SHADE_LOOP
-#define NDT_SHADE_LOOP 1      /* 1: fixed grid striding over the batch; 0: one thread per ray of a FULL batch, early exit */
+#define NDT_SHADE_LOOP 1      /* 1: fixed grid, dynamic draw; 0: one thread per ray of a FULL batch, early exit */
 #endif
-template <int NP, int PHASE>
-__device__ __forceinline__ void shade_one(
-const Scene &sc, const WaveArgs &a, WaveState *st, int r, int lane,
-                                       unsigned long long &shadow_total)
+
+/* the answer slot of a (ray, light) pair goes through three states: HitRec (k_trace<1>), LightGeo (k_light),
+ * LightTerm (k_libm); all 32 bytes */
+struct alignas(16) LightGeo { double q, ldist2, rvdot; int32_t lit, qok; };
+struct alignas(16) LightTerm { double light_scale, rvn; int32_t lit, pad; double pad2; };
+
+template <int NP> __device__ __forceinline__ void hgeo_store_s(double2 *base, size_t stride, size_t e, const double *Hp, const double *Hn)
 {
-    const int gen = st->gen, start = st->start, count = st->count;
+    double2 *d = base + e;
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) d[(size_t)(i / 2) * stride] = make_double2(Hp[i], Hp[i + 1]);
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) d[(size_t)(NP / 2 + i / 2) * stride] = make_double2(Hn[i], Hn[i + 1]);
+}
+template <int NP> __device__ __forceinline__ void hgeo_load_s(const double2 *base, size_t stride, size_t e, double *Hp, double *Hn)
+{
+    const double2 *d = base + e;
+    double2 t[NP];
+    NDT_UNROLL
+    for (int i = 0; i < NP; ++i) t[i] = d[(size_t)i * stride];
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) { Hp[i] = t[i / 2].x; Hp[i + 1] = t[i / 2].y; }
+    NDT_UNROLL
+    for (int i = 0; i < NP; i += 2) { Hn[i] = t[NP / 2 + i / 2].x; Hn[i + 1] = t[NP / 2 + i / 2].y; }
+}
+
+/* phase A, one ray */
+template <int NP>
+__device__ __forceinline__ void shade_a_one(const Scene &sc, const WaveArgs &a, WaveState *st, const WaveHead *hd, int r, int lane)
+{
+    const int gen = hd->gen, start = hd->start, count = hd->count;
     const int nl = sc.n_lights;
     double o[NP], v[NP], frac;
     int depth, tx, ty;
@@ -508,19 +624,8 @@ const Scene &sc, const WaveArgs &a, WaveState *st, int r, int lane,
      * hit record): start them before the ray is rebuilt */
     Hit T0;
     T0.t = -1; T0.id = -1; T0.win = -1; T0.found = 0;
-    if (r < count) hit_load(a.hits + (start + r), T0.t, T0.id, T0.win, T0.found);
-    /* phase B: the answers of the first lights as well (k_shade is latency bound: ncu long_scoreboard 41 %,
-     * the slot -> answer chain of every light was on the critical path) */
-    constexpr int PF = 3;
-    Hit P[PF];
-    if (PHASE == 1) {
-        NDT_UNROLL
-        for (int k = 0; k < PF; ++k) {
-            P[k].t = -1; P[k].id = -1; P[k].win = -1; P[k].found = 0;
-            if (r < count && k < nl) hit_load(a.shits + ((size_t)r * nl + k), P[k].t, P[k].id, P[k].win, P[k].found);
-        }
-    }
-    const bool active = wave_ray<NP>(sc, a, st, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+    if (r < count) hit_load_s(a.hits, (size_t)a.cap, (size_t)(start + r), T0.t, T0.id, T0.win, T0.found);
+    const bool active = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
     Tally<false> none;
     Shade<NP> S;
     RayRec rec;
@@ -532,45 +637,110 @@ const Scene &sc, const WaveArgs &a, WaveState *st, int r, int lane,
     if (active) {
         shade_setup<NP, false>(sc, S, -1, o, v, nsh, none);
         shade_after<NP, false>(sc, S, -1, T0, o, v, rec, p_hit, p_id, p_dist, none);
+        if (S.shaded) hgeo_store_s<NP>(a.hgeo, (size_t)a.gen_cap, (size_t)r, S.Hp, S.Hn);
     }
+    /* which lights were asked: bit 0 = the ray is shaded at all, bit 1 + it = light it has a query */
+    uint32_t mword = (active && S.shaded) ? 1u : 0u;
+    uint32_t *mrow = a.qmask + r;            /* word w at mrow[w * gen_cap] */
+    int mw_idx = 0;
     if (__ballot_sync(FULL, active && S.shaded)) {
         for (int it = 0; it < nl; ++it) {
             const bool want = active && shade_setup<NP, false>(sc, S, it, o, v, nsh, none);
-            if (PHASE == 0) {
-                /* slots of this light's queries: one ballot, one atomic per warp; queries of one
-                 * light from neighbouring pixels end up next to each other in the queue */
-                const unsigned b = __ballot_sync(FULL, want);
-                int wbase = 0;
-                if (b) {
-                    if (lane == 0) wbase = atomicAdd(&st->stail, __popc(b));
-                    wbase = __shfl_sync(FULL, wbase, 0);
-                }
-                if (active) {
-                    int slot = -1;
-                    if (want) {
-                        slot = wbase + __popc(b & ((1u << lane) - 1u));
-                        if (slot < a.scap) {
-                            /* depth = light index + 1 for the any-hit query of a DIRECTIONAL light */
-                            ray_store<NP>((RayIn<NP> *)a.srays + slot, S.ro, S.rv, S.limit,
-                                          S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0, r * nl + it);
-                        } else {
-                            atomicExch(&st->pool_overflow, 2);   /* the render fails with NDT_B200_E_OVERFLOW */
-                        }
-                    }
-                }
-            } else if (want) {
-                Hit T;
-                if (it < PF) {
-                    T = it == 0 ? P[0] : (it == 1 ? P[1] : P[2]);
+            /* slots of this light's queries: one ballot, one atomic per warp; queries of one
+             * light from neighbouring pixels end up next to each other in the queue */
+            const unsigned b = __ballot_sync(FULL, want);
+            int wbase = 0;
+            if (b) {
+                if (lane == 0) wbase = atomicAdd(&st->stail, __popc(b));
+                wbase = __shfl_sync(FULL, wbase, 0);
+            }
+            if (want) {
+                const int slot = wbase + __popc(b & ((1u << lane) - 1u));
+                if (slot < a.scap) {
+                    /* depth = light index + 1 for the any-hit query of a DIRECTIONAL light */
+                    ray_store_s<NP>(a.srays, (size_t)a.scap, (size_t)slot, S.ro, S.rv, S.limit,
+                                    S.ltype == NDT_L_DIRECTIONAL ? 1 + it : 0, it * a.gen_cap + r);
                 } else {
-                    hit_load(a.shits + ((size_t)r * nl + it), T.t, T.id, T.win, T.found);
+                    atomicExch(&st->pool_overflow, 2);   /* the render fails with NDT_B200_E_OVERFLOW */
                 }
-                shade_after<NP, false>(sc, S, it, T, o, v, rec, p_hit, p_id, p_dist, none);
+                mword |= 1u << ((it + 1) & 31);
+            }
+            if (((it + 2) & 31) == 0) {         /* the word is full */
+                if (r < count) mrow[(size_t)mw_idx * a.gen_cap] = mword;
+                ++mw_idx; mword = 0;
             }
         }
     }
-    if (PHASE == 0) return;
+    if (r < count) {
+        mrow[(size_t)mw_idx * a.gen_cap] = mword;
+        for (int w = mw_idx + 1; w < (int)a.mw; ++w) mrow[(size_t)w * a.gen_cap] = 0;
+    }
+    if (gen == 0 && hd->samples_xy == nullptr && r < count) {
+        const int tw = hd->tw, th = hd->th;
+        if (tx < tw && ty < th) {
+            /* !active: a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
+            const size_t p = (size_t)ty * tw + tx;
+            uint8_t *oh = hd->out_hit;
+            int32_t *oi = hd->out_id;
+            double *od = hd->out_depth;
+            if (oh) oh[p] = active ? (uint8_t)p_hit : 0;
+            if (oi) oi[p] = active ? p_id : -1;
+            if (od) od[p] = (active && p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
+        }
+    }
+}
 
+/* phase B, one ray */
+template <int NP>
+__device__ __forceinline__ void shade_b_one(const Scene &sc, const WaveArgs &a, WaveState *st, const WaveHead *hd, int r, int lane,
+                                            unsigned long long &shadow_total)
+{
+    const int gen = hd->gen, start = hd->start, count = hd->count;
+    const int nl = sc.n_lights;
+    double o[NP], v[NP], frac;
+    int depth, tx, ty;
+    Hit T0;
+    T0.t = -1; T0.id = -1; T0.win = -1; T0.found = 0;
+    uint32_t mword = 0;
+    const uint32_t *mrow = a.qmask + r;
+    if (r < count) {
+        hit_load_s(a.hits, (size_t)a.cap, (size_t)(start + r), T0.t, T0.id, T0.win, T0.found);
+        mword = mrow[0];
+    }
+    const bool active = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+    Tally<false> none;
+    Shade<NP> S;
+    RayRec rec;
+    Spawn<NP> sp;
+    shade_init<NP>(S, rec, sp);
+    uint32_t nsh = 0;
+    if (active && (mword & 1u)) {
+        /* what shade_after(-1) left in S, without the intersection */
+        S.shaded = true;
+        S.oid = T0.id;
+        hgeo_load_s<NP>(a.hgeo, (size_t)a.gen_cap, (size_t)r, S.Hp, S.Hn);
+        const ndt_flat_object *fo = sc.obj + S.oid;
+        S.hr = NDT_LDG(&fo->rgb[0]); S.hg = NDT_LDG(&fo->rgb[1]); S.hb = NDT_LDG(&fo->rgb[2]);
+        rec.h[0] = NDT_LDG(&fo->refl[0]); rec.h[1] = NDT_LDG(&fo->refl[1]); rec.h[2] = NDT_LDG(&fo->refl[2]);
+        if (sc.specular) { S.rr = rec.h[0]; S.rg = rec.h[1]; S.rb = rec.h[2]; }
+        S.transparent = (NDT_LDG(&fo->flags) & NDT_OF_TRANSPARENT) != 0;
+        S.clr0 = S.hr * sc.ambient[0];                               /* ndt.c:88-92 */
+        S.clr1 = S.hg * sc.ambient[1];
+        S.clr2 = S.hb * sc.ambient[2];
+        int mw_idx = 0;
+        for (int it = 0; it < nl; ++it) {                            /* ndt.c:103-310, the reference's order */
+            const ndt_flat_light *L = sc.lights + it;
+            if (NDT_LDG(&L->type) == NDT_L_AMBIENT) {                /* ndt.c:105-111 */
+                S.clr0 += S.hr * NDT_LDG(&L->rgb[0]); S.clr1 += S.hg * NDT_LDG(&L->rgb[1]); S.clr2 += S.hb * NDT_LDG(&L->rgb[2]);
+            } else if (mword & (1u << ((it + 1) & 31))) {
+                ++nsh;
+                const size_t e = (size_t)it * a.gen_cap + r;
+                const double2 t0 = a.shits[e], t1 = a.shits[(size_t)a.gen_cap * a.nl_eff + e];
+                if (__double2loint(t1.y)) light_apply<NP>(sc, S, L, t0.x, t0.y);      /* lit (k_light), scale and rvn (k_libm) */
+            }
+            if (((it + 2) & 31) == 0) mword = mrow[(size_t)(++mw_idx) * a.gen_cap];
+        }
+    }
     if (active) {
         shade_finish<NP, false>(sc, S, v, frac, depth, rec, sp, none);
         rec.nrays = 1u + nsh;
@@ -589,89 +759,147 @@ const Scene &sc, const WaveArgs &a, WaveState *st, int r, int lane,
     const bool fits = wbase + total <= a.cap;
     if (total > 0 && !fits && lane == 0) atomicExch(&st->pool_overflow, 1);
     const unsigned lt = (1u << lane) - 1u;
-    RayIn<NP> *rays = (RayIn<NP> *)a.rays;
-    const int n0 = ld_here(&st->n0);
-    const bool pixels = gen == 0 && ld_here(&st->samples_xy) == nullptr;
+    const int n0 = hd->n0;
     if (active) {
         if (sp.want_refl == 2) rec.child_refl = CHILD_BLACK;
         if (sp.want_refr == 2) rec.child_refr = CHILD_BLACK;
         if (q1) {
             const int s = wbase + __popc(b1 & lt);
             rec.child_refl = fits ? s : CHILD_BLACK;
-            if (fits) {
-                ray_store<NP>(rays + (s - n0), sp.origin, sp.refl_dir, sp.refl_frac, depth - 1);
-            }
+            if (fits) ray_store_s<NP>(a.rays, (size_t)a.cap, (size_t)(s - n0), sp.origin, sp.refl_dir, sp.refl_frac, depth - 1);
         }
         if (q2) {
             const int s = wbase + __popc(b1) + __popc(b2 & lt);
             rec.child_refr = fits ? s : CHILD_BLACK;
-            if (fits) {
-                ray_store<NP>(rays + (s - n0), sp.origin, sp.refr_dir, sp.refr_frac, depth - 1);
-            }
+            if (fits) ray_store_s<NP>(a.rays, (size_t)a.cap, (size_t)(s - n0), sp.origin, sp.refr_dir, sp.refr_frac, depth - 1);
         }
-        rec_store(a.rec + (start + r), rec);
-        if (pixels) {
-            const size_t p = (size_t)ty * ld_here(&st->tw) + tx;
-            uint8_t *oh = ld_here(&st->out_hit);
-            int32_t *oi = ld_here(&st->out_id);
-            double *od = ld_here(&st->out_depth);
-            if (oh) oh[p] = (uint8_t)p_hit;
-            if (oi) oi[p] = p_id;
-            if (od) od[p] = (p_id >= 0 && p_dist > EPS) ? 1.0 / p_dist : 0.0;
-        }
+        rec_store_s(a.rec, (size_t)a.cap, (size_t)(start + r), rec);
     } else if (gen == 0 && r < count) {
         /* padding lane of a partial 8x4 block: keep the record defined */
         RayRec z;
         z.clr[0] = z.clr[1] = z.clr[2] = 0.0; z.alpha = 0.0;
         z.h[0] = z.h[1] = z.h[2] = 0.0;
         z.child_refl = z.child_refr = CHILD_NONE; z.nrays = 0; z.flags = REC_UNTRACED;
-        rec_store(a.rec + (start + r), z);
-        if (pixels && tx < ld_here(&st->tw) && ty < ld_here(&st->th)) {   /* a pixel of the frame that is not traced (HIDEF_3D blanking rows) */
-            const size_t p = (size_t)ty * ld_here(&st->tw) + tx;
-            uint8_t *oh = ld_here(&st->out_hit);
-            int32_t *oi = ld_here(&st->out_id);
-            double *od = ld_here(&st->out_depth);
-            if (oh) oh[p] = 0;
-            if (oi) oi[p] = -1;
-            if (od) od[p] = 0.0;
-        }
+        rec_store_s(a.rec, (size_t)a.cap, (size_t)(start + r), z);
     }
     shadow_total += active ? nsh : 0;
 }
 
-/* The grid is fixed (it sits in a CUDA graph); a warp strides over the batch.  Inside the striding loop ptxas
- * hoists the loop-invariant scene loads (lights, materials) out of the loop and keeps them in registers: +40 to
- * +60 registers, one CTA per SM less, k_shade<4,B> 3.3 -> 4.6 ms on BASELINE config 1 (profiles/r02_*).  The
- * launch bounds pin each instantiation to the occupancy of its loop-free form (register counts of that form:
- * 105 / 124 / 164 / 208 / 190 for phase A and 168 / 222 / 255 / 255 / 255 for phase B at NP = 4 ... 12). */
+/* Inside the drawing loop ptxas hoists loop-invariant scene loads (lights, materials) out of the loop and
+ * keeps them in registers: +40 to +60 registers and one CTA per SM less than the loop-free form (ptxas -v;
+ * k_shade<4,B> 3.3 -> 4.6 ms on BASELINE config 1).  The launch bounds pin the occupancy. */
 template <int NP, int PHASE> __host__ __device__ constexpr int shade_min_blocks()
 {
+#ifdef NDT_SHADE_A_BLOCKS
+    if (PHASE == 0) return NDT_SHADE_A_BLOCKS;
+#endif
 #ifdef NDT_SHADE_MIN_BLOCKS
     return NDT_SHADE_MIN_BLOCKS;
 #else
-    return PHASE == 0 ? (NP <= 6 ? 4 : (NP <= 8 ? 3 : 2)) : (NP <= 4 ? 3 : 2);
+#ifdef NDT_SHADE_NO_BOUNDS
+    return 1;
+#else
+    return PHASE == 0 ? (NP <= 4 ? 4 : (NP <= 8 ? 3 : 2)) : (NP <= 6 ? 4 : (NP <= 8 ? 3 : 2));
+#endif
 #endif
 }
 template <int NP, int PHASE>
-__global__ void __launch_bounds__(BLOCK, shade_min_blocks<NP, PHASE>()) k_shade(
-const Scene sc, const WaveArgs a)
+__global__ void __launch_bounds__(BLOCK, shade_min_blocks<NP, PHASE>()) k_shade(const Scene sc, const WaveArgs a)
 {
     const int lane = threadIdx.x & 31;
-    const int count = a.st->count;
+    const WaveHead *hd = wave_head_load(a.st);
+    const int count = hd->count;
     unsigned long long shadow_total = 0;
-#if NDT_SHADE_LOOP
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r - lane < count; r += gridDim.x * blockDim.x)
-        shade_one<NP, PHASE>(sc, a, a.st, r, lane, shadow_total);
+#if defined(NDT_SHADE_STATIC)
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r - lane < count; r += gridDim.x * blockDim.x) {
+        if (PHASE == 0) shade_a_one<NP>(sc, a, a.st, hd, r, lane);
+        else shade_b_one<NP>(sc, a, a.st, hd, r, lane, shadow_total);
+    }
+#elif NDT_SHADE_LOOP
+    /* 128 rays per draw: the round trip of the atomic is exposed (nothing else to do in the warp), one per
+     * 32 rays was 10 % of the stall samples */
+    int *next = PHASE ? &a.st->nextB : &a.st->nextA;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(next, 128);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        for (int k = 0; k < 4 && base + 32 * k < count; ++k) {
+            if (PHASE == 0) shade_a_one<NP>(sc, a, a.st, hd, base + 32 * k + lane, lane);
+            else shade_b_one<NP>(sc, a, a.st, hd, base + 32 * k + lane, lane, shadow_total);
+        }
+    }
 #else
     {
         const int r = blockIdx.x * blockDim.x + threadIdx.x;
         if (r - lane >= count) return;
-        shade_one<NP, PHASE>(sc, a, a.st, r, lane, shadow_total);
+        if (PHASE == 0) shade_a_one<NP>(sc, a, a.st, hd, r, lane);
+        else shade_b_one<NP>(sc, a, a.st, hd, r, lane, shadow_total);
     }
 #endif
     if (PHASE == 0) return;
     for (int d = 16; d > 0; d >>= 1) shadow_total += __shfl_down_sync(FULL, shadow_total, d);
     if (lane == 0 && shadow_total) atomicAdd(&a.stats[0], shadow_total);
+}
+
+/* the vector half of the lit term, one shadow query per thread */
+template <int NP>
+__global__ void __launch_bounds__(BLOCK, 3) k_light(const Scene sc, const WaveArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    WaveState *st = a.st;
+    const WaveHead *hd = wave_head_load(st);
+    const int gen = hd->gen, start = hd->start, count = hd->count;
+    int nq = *(volatile const int *)&st->stail;
+    if (nq > a.scap) nq = a.scap;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&st->nextL, 128);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= nq) break;
+        for (int k = 0; k < 4; ++k) {
+        const int j = base + 32 * k + lane;
+        if (j >= nq) continue;
+        double ro[NP], rv[NP], limit;
+        int code;
+        int aux;
+        ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)j, ro, rv, limit, code, aux);
+        const int it = aux / a.gen_cap, r = aux - it * a.gen_cap;
+        const size_t sstride = (size_t)a.gen_cap * a.nl_eff;
+        Hit T;
+        hit_load_s(a.shits, sstride, (size_t)aux, T.t, T.id, T.win, T.found);
+        const ndt_flat_light *L = sc.lights + it;
+        const int ltype = NDT_LDG(&L->type);
+        LightGeo out;
+        out.q = 0.0; out.ldist2 = 1.0; out.rvdot = 0.0; out.lit = 0; out.qok = 0;
+        /* the cheap rejections first (ndt.c:217, 241): most shadowed pairs stop here */
+        double t0; int oid, owin, ofound;
+        hit_load_s(a.hits, (size_t)a.cap, (size_t)(start + r), t0, oid, owin, ofound);
+        const bool maybe = ltype == NDT_L_DIRECTIONAL ? !T.found : (T.found && T.id == oid);
+        if (maybe) {
+            double Hp[NP], Hn[NP], o[NP], v[NP], frac, lv[NP];
+            int depth, tx, ty;
+            hgeo_load_s<NP>(a.hgeo, (size_t)a.gen_cap, (size_t)r, Hp, Hn);
+            /* the ray's direction (ndt.c:296 needs -look): rebuilt like every other kernel does */
+            wave_ray<NP>(sc, a, hd, gen, start, count, r, (start + r) & 31, o, v, frac, depth, tx, ty);
+            if (ltype != NDT_L_DIRECTIONAL) {
+                /* light_vec and ldist2 as shade_setup computed them (ndt.c:194-197): the query carries the light's
+                 * position (ro) and the unit vector (rv); |Hp - lgt_pos|^2 is the same subtraction and dot product */
+                double d[NP];
+                vsub<NP>(Hp, ro, d);
+                out.ldist2 = vdot<NP>(d, d);
+                vcopy<NP>(lv, rv);
+            }
+            Tally<false> none;
+            double q, rvdot; int qok;
+            if (light_geom<NP, false>(sc, L, ltype, oid, Hp, Hn, ro, rv, lv, T, v, q, qok, rvdot, none)) {
+                out.q = q; out.qok = qok; out.rvdot = rvdot; out.lit = 1;
+            }
+        }
+        a.shits[aux] = make_double2(out.q, out.ldist2);
+        a.shits[sstride + aux] = make_double2(out.rvdot, __hiloint2double(out.qok, out.lit));
+        }
+    }
 }
 
 /* trace_kd (object.c:683) for an explicit list of rays: the probe behind
@@ -738,5 +966,7 @@ struct NpOps {
     const void *(*shade_fn)(int phase);
     size_t (*trace_smem_bytes)(bool boxed);
     int (*shade_grid)(int sm_count, int gen_cap);   /* blocks of a k_shade launch */
+    const void *(*light_fn)();
+    void (*light)(int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
 };
 const NpOps *ndt_np_ops(int np);     /* NULL: dimension not built */

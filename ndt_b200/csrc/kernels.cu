@@ -110,6 +110,35 @@ __global__ void k_finish(RayRec *rec, int tw, int th, int bpr, int specular,
     }
 }
 
+constexpr unsigned FULL_MASK = 0xffffffffu;
+/* the scalar half: acos, cos, pow (ndt.c:261-268, 300) per lit pair */
+__global__ void __launch_bounds__(256) k_libm(const WaveArgs a, int specular, int aux_word)
+{
+    const int lane = threadIdx.x & 31;
+    WaveState *st = a.st;
+    int nq = *(volatile const int *)&st->stail;
+    if (nq > a.scap) nq = a.scap;
+    const size_t sstride = (size_t)a.gen_cap * a.nl_eff;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&st->nextM, 128);
+        base = __shfl_sync(FULL_MASK, base, 0);
+        if (base >= nq) break;
+        for (int k = 0; k < 4; ++k) {
+            const int j = base + 32 * k + lane;
+            if (j >= nq) continue;
+            /* where the answer of query j lives: the high word of its last 16-byte word (ray_store_s) */
+            const int aux = __double2hiint(a.srays[(size_t)aux_word * a.scap + j].y);
+            const double2 g0 = a.shits[aux], g1 = a.shits[sstride + aux];
+            const int lit = __double2loint(g1.y), qok = __double2hiint(g1.y);
+            if (!lit) continue;
+            double light_scale, rvn;
+            light_libm(g0.x, qok, g0.y, g1.x, specular, light_scale, rvn);
+            a.shits[aux] = make_double2(light_scale, rvn);
+        }
+    }
+}
+
 /* ---- bookkeeping kernels of the device-side generation loop (one thread each) ---- */
 __global__ void k_begin(WaveState *st, const WaveBegin b, int gen_cap, unsigned long long *stats)
 {
@@ -122,7 +151,7 @@ __global__ void k_begin(WaveState *st, const WaveBegin b, int gen_cap, unsigned 
     st->gen = 0; st->start = 0; st->count = b.n0 < gen_cap ? b.n0 : gen_cap;
     st->gen_start = 0; st->gen_count = b.n0;
     st->ngen = 0; st->iters = 0; st->cont = 1; st->resolve_g = 0; st->fail = 0;
-    st->tail = b.n0; st->next0 = 0; st->stail = 0; st->next1 = 0;
+    st->tail = b.n0; st->next0 = 0; st->stail = 0; st->next1 = 0; st->nextA = 0; st->nextB = 0; st->nextR = 0; st->nextF = 0; st->nextL = 0; st->nextM = 0;
     st->pool_overflow = 0; st->kd_fault = 0;
     if (b.first) for (int k = 0; k < 8; ++k) stats[k] = 0ull;
 }
@@ -161,7 +190,7 @@ __global__ void k_next_gen(WaveState *st, int cap, int gen_cap, cudaGraphConditi
             }
         }
     }
-    st->next0 = 0; st->stail = 0; st->next1 = 0;
+    st->next0 = 0; st->stail = 0; st->next1 = 0; st->nextA = 0; st->nextB = 0; st->nextL = 0; st->nextM = 0;
     st->cont = cont;
     if (!cont) st->fail = st->pool_overflow | (st->kd_fault << 8);
     if (use_h) cudaGraphSetConditional(h, cont ? 1u : 0u);
@@ -173,6 +202,7 @@ __global__ void k_pre_resolve(WaveState *st, cudaGraphConditionalHandle h, int u
     if (threadIdx.x || blockIdx.x) return;
     const int g = st->fail ? 0 : st->ngen - 1;
     st->resolve_g = g;
+    st->nextR = 0; st->nextF = 0;
     if (use_h) cudaGraphSetConditional(h, g >= 1 ? 1u : 0u);
 }
 __global__ void k_resolve_next(WaveState *st, cudaGraphConditionalHandle h, int use_h)
@@ -180,61 +210,86 @@ __global__ void k_resolve_next(WaveState *st, cudaGraphConditionalHandle h, int 
     if (threadIdx.x || blockIdx.x) return;
     const int g = st->resolve_g - 1;
     st->resolve_g = g;
+    st->nextR = 0;
     if (use_h) cudaGraphSetConditional(h, g >= 1 ? 1u : 0u);
 }
 
 /* the same two kernels for the device-side loop: what to fold comes from WaveState, the grids are fixed */
-__global__ void k_resolve_dev(RayRec *rec, const WaveState *st, int specular)
+/* the children's colours and ray counts: words 0, 1 and 4 of their records */
+__device__ __forceinline__ void child_load(RayRec &c, const double2 *rec, size_t cap, int slot)
+{
+    double2 *d = reinterpret_cast<double2 *>(&c);
+    d[0] = rec[slot];
+    d[1] = rec[cap + slot];
+    d[4] = rec[4 * cap + slot];
+}
+
+__global__ void k_resolve_dev(double2 *rec, int cap, WaveState *st, int specular)
 {
     if (st->fail) return;
     const int g = st->resolve_g;
     const int start = st->gstart[g], count = st->gcount[g];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        RayRec r;
-        rec_load(r, rec + start + i);
-        if (r.child_refl == CHILD_NONE && r.child_refr == CHILD_NONE) continue;
-        const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
-        const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
-        resolve_rec(r, c1, c2, specular);
-        rec_store(rec + start + i, r);
+    const int lane = threadIdx.x & 31;
+    while (true) {      /* 128 records per warp and draw */
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&st->nextR, 128);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        for (int k = 0; k < 4; ++k) {
+            const int i = base + 32 * k + lane;
+            if (i >= count) continue;
+            RayRec r, c1, c2;
+            rec_load_s(r, rec, (size_t)cap, (size_t)(start + i));
+            if (r.child_refl == CHILD_NONE && r.child_refr == CHILD_NONE) continue;
+            if (r.child_refl >= 0) child_load(c1, rec, (size_t)cap, r.child_refl);
+            if (r.child_refr >= 0) child_load(c2, rec, (size_t)cap, r.child_refr);
+            resolve_rec(r, r.child_refl >= 0 ? &c1 : nullptr, r.child_refr >= 0 ? &c2 : nullptr, specular);
+            rec_store_s(rec, (size_t)cap, (size_t)(start + i), r);
+        }
     }
 }
 
-__global__ void k_finish_dev(RayRec *rec, const WaveState *st, int specular, unsigned long long *stats)
+__global__ void __launch_bounds__(256, 4) k_finish_dev(double2 *rec, int cap, WaveState *st, int specular, unsigned long long *stats)
 {
     if (st->fail) return;
     const int tw = st->tw, th = st->th, bpr = st->bpr;
     double *out_f64 = st->out_f64;
     uint8_t *out_u8 = st->out_u8;
     unsigned long long rays_ref = 0, samples = 0, hits = 0, traced = 0;
-    /* every warp runs the same number of iterations (the shuffles below need all 32 lanes) */
-    const int n = tw * th, np32 = (n + 31) & ~31;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np32; p += gridDim.x * blockDim.x) {
-        if (p >= n) continue;
-        const int tx = p % tw, ty = p / tw;
-        /* bpr == 0: a sample list, record r belongs to sample r */
-        const int slot = bpr ? ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7) : p;
-        RayRec r;
-        rec_load(r, rec + slot);
-        const RayRec *c1 = r.child_refl >= 0 ? rec + r.child_refl : nullptr;
-        const RayRec *c2 = r.child_refr >= 0 ? rec + r.child_refr : nullptr;
-        resolve_rec(r, c1, c2, specular);
-        double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4] = { 0.0, 0.0, 0.0, 0.0 };
-        /* a pixel render_pixel leaves black without calling get_pixel_color has no sample loop */
-        const int ns = (r.flags & REC_UNTRACED) ? 0 : replay_samples(l, o);
-        if (out_f64) {
-            double2 *d = reinterpret_cast<double2 *>(out_f64 + 4 * (size_t)p);
-            d[0] = make_double2(o[0], o[1]);
-            d[1] = make_double2(o[2], o[3]);
+    const int n = tw * th, lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&st->nextF, 128);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        for (int k = 0; k < 4; ++k) {
+            const int p = base + 32 * k + lane;
+            if (p >= n) continue;
+            const int tx = p % tw, ty = p / tw;
+            /* bpr == 0: a sample list, record r belongs to sample r */
+            const int slot = bpr ? ((ty >> 2) * bpr + (tx >> 3)) * 32 + ((ty & 3) << 3) + (tx & 7) : p;
+            RayRec r, c1, c2;
+            rec_load_s(r, rec, (size_t)cap, (size_t)slot);
+            if (r.child_refl >= 0) child_load(c1, rec, (size_t)cap, r.child_refl);
+            if (r.child_refr >= 0) child_load(c2, rec, (size_t)cap, r.child_refr);
+            resolve_rec(r, r.child_refl >= 0 ? &c1 : nullptr, r.child_refr >= 0 ? &c2 : nullptr, specular);
+            double l[4] = { r.clr[0], r.clr[1], r.clr[2], r.alpha }, o[4] = { 0.0, 0.0, 0.0, 0.0 };
+            /* a pixel render_pixel leaves black without calling get_pixel_color has no sample loop */
+            const int ns = (r.flags & REC_UNTRACED) ? 0 : replay_samples(l, o);
+            if (out_f64) {
+                double2 *d = reinterpret_cast<double2 *>(out_f64 + 4 * (size_t)p);
+                d[0] = make_double2(o[0], o[1]);
+                d[1] = make_double2(o[2], o[3]);
+            }
+            if (out_u8) {
+                uchar4 c = make_uchar4(d2c(o[0]), d2c(o[1]), d2c(o[2]), d2c(o[3]));
+                reinterpret_cast<uchar4 *>(out_u8)[p] = c;
+            }
+            rays_ref += (unsigned long long)r.nrays * (unsigned long long)ns;
+            samples += (unsigned long long)ns;
+            hits += r.flags & 1u;
+            traced += (r.flags & REC_UNTRACED) ? 0 : 1;
         }
-        if (out_u8) {
-            uchar4 c = make_uchar4(d2c(o[0]), d2c(o[1]), d2c(o[2]), d2c(o[3]));
-            reinterpret_cast<uchar4 *>(out_u8)[p] = c;
-        }
-        rays_ref += (unsigned long long)r.nrays * (unsigned long long)ns;
-        samples += (unsigned long long)ns;
-        hits += r.flags & 1u;
-        traced += (r.flags & REC_UNTRACED) ? 0 : 1;
     }
     for (int d = 16; d > 0; d >>= 1) {
         rays_ref += __shfl_down_sync(0xffffffffu, rays_ref, d);
@@ -242,7 +297,7 @@ __global__ void k_finish_dev(RayRec *rec, const WaveState *st, int specular, uns
         hits += __shfl_down_sync(0xffffffffu, hits, d);
         traced += __shfl_down_sync(0xffffffffu, traced, d);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (rays_ref) atomicAdd(&stats[2], rays_ref);
         if (samples) atomicAdd(&stats[3], samples);
         if (hits) atomicAdd(&stats[4], hits);
@@ -279,7 +334,7 @@ template <bool FUSED> __global__ void k_fp64_probe(double *sink, int iters)
     return ndt_set_error(NDT_B200_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 /* what ndt_b200_sync reads back of a pass: WaveState up to (not including) gstart[] */
-#define WAVE_HEAD_BYTES offsetof(WaveState, gstart)
+#define WAVE_HEAD_BYTES (sizeof(WaveState) - 2 * WAVE_MAX_GEN * sizeof(int))
 
 struct WaveGraph {
     cudaGraph_t graph;
@@ -308,6 +363,8 @@ struct ndt_b200_ctx {
     HitRec *d_hits; size_t hits_cap;     /* one per record slot */
     char *d_srays; size_t srays_bytes;   /* shadow queries of one batch */
     HitRec *d_shits; size_t shits_cap;
+    double *d_hgeo; size_t hgeo_bytes;   /* hit point + normal per ray of a batch */
+    uint32_t *d_qmask; size_t qmask_bytes;
     int trace_grid[2][8];                /* cached k_trace occupancy per (boxed scene, NP/2) */
     char *d_ana; size_t ana_bytes;       /* ANAGLYPH_3D: the two eyes' fp64 frames */
     int *d_ctr;                          /* fused path: [0] tail [1] next [2..3] overflow */
@@ -402,7 +459,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
-    cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits);
+    cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_hgeo); cudaFree(c->d_qmask);
     cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out); cudaFree(c->d_state);
     cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats); cudaFreeHost(c->h_snap);
     if (c->wg.exec) cudaGraphExecDestroy(c->wg.exec);
@@ -560,7 +617,8 @@ static int ensure_pools(ndt_b200_ctx *c, int n0, int np, int grid_threads)
         if ((r = grow_pool(c, (void **)&c->d_rec, &bytes, want * sizeof(RayRec)))) { c->rec_cap = 0; return r; }
         c->rec_cap = bytes / sizeof(RayRec);
     }
-    if ((r = grow_pool(c, &c->d_rays, &c->rays_bytes, (c->rec_cap - (size_t)n0 + 1) * rayin_bytes(np)))) return r;
+    /* word-major with stride = pool capacity (gen.cuh): a full capacity's worth of entries */
+    if ((r = grow_pool(c, &c->d_rays, &c->rays_bytes, c->rec_cap * rayin_bytes(np)))) return r;
     size_t words = ((size_t)c->hdr.n_items + 31) / 32;
     if (words == 0) words = 1;
     if ((r = grow_pool(c, (void **)&c->d_mb, &c->mb_bytes, words * (size_t)grid_threads * sizeof(uint32_t)))) return r;
@@ -622,6 +680,10 @@ extern "C" int ndt_b200_launch_tile(ndt_b200_ctx *c, int x0, int y0, int tw, int
     return 0;
 }
 
+/* grids of the per-query kernels: enough CTAs to fill the GPU, the warps draw their work */
+static int light_grid(const ndt_b200_ctx *c) { return c->sm_count * 6; }
+static int libm_grid(const ndt_b200_ctx *c) { return c->sm_count * 8; }
+
 /* ---- the CUDA graph of one pass (see the header of this file) ------------------------------------ */
 static void wave_graph_drop(ndt_b200_ctx *c)
 {
@@ -669,7 +731,13 @@ static int wave_graph_build(ndt_b200_ctx *c, int np, const WaveArgs &a, int n_sh
     void *targs[] = { &sc, &wa };
     GK(add_kernel(b1, &n_prev, NULL, ops->trace_fn(0), trace_grid, BLOCK, smem, targs));
     GK(add_kernel(b1, &n_cur, &n_prev, ops->shade_fn(0), shade_grid, BLOCK, 0, targs)); n_prev = n_cur;
-    if (n_sh > 0) { GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(1), trace_grid, BLOCK, smem, targs)); n_prev = n_cur; }
+    if (n_sh > 0) {
+        GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(1), trace_grid, BLOCK, smem, targs)); n_prev = n_cur;
+        GK(add_kernel(b1, &n_cur, &n_prev, ops->light_fn(), light_grid(c), BLOCK, 0, targs)); n_prev = n_cur;
+        int spec = c->hdr.specular, aux_word = np;
+        void *largs[] = { &wa, &spec, &aux_word };
+        GK(add_kernel(b1, &n_cur, &n_prev, (const void *)k_libm, libm_grid(c), 256, 0, largs)); n_prev = n_cur;
+    }
     GK(add_kernel(b1, &n_cur, &n_prev, ops->shade_fn(1), shade_grid, BLOCK, 0, targs)); n_prev = n_cur;
     WaveState *st = c->d_state;
     int cap = a.cap, gen_cap = a.gen_cap, use_h = 1;
@@ -687,17 +755,17 @@ static int wave_graph_build(ndt_b200_ctx *c, int np, const WaveArgs &a, int n_sh
     p2.conditional.handle = h2; p2.conditional.type = cudaGraphCondTypeWhile; p2.conditional.size = 1;
     GK(cudaGraphAddNode(&loop2, w.graph, &pre, 1, &p2));
     cudaGraph_t b2 = p2.conditional.phGraph_out[0];
-    RayRec *rec = a.rec;
+    double2 *rec = a.rec;
     int specular = c->hdr.specular;
     unsigned long long *stats = c->d_stats;
     {
-        void *args[] = { &rec, &st, &specular };
+        void *args[] = { &rec, &cap, &st, &specular };
         GK(add_kernel(b2, &n_prev, NULL, (const void *)k_resolve_dev, c->sm_count * 4, 256, 0, args));
         void *args2[] = { &st, &h2, &use_h };
         GK(add_kernel(b2, &n_cur, &n_prev, (const void *)k_resolve_next, 1, 32, 0, args2));
     }
     {
-        void *args[] = { &rec, &st, &specular, &stats };
+        void *args[] = { &rec, &cap, &st, &specular, &stats };
         GK(add_kernel(w.graph, &fin, &loop2, (const void *)k_finish_dev, c->sm_count * 8, 256, 0, args));
     }
     GK(cudaGraphInstantiate(&w.exec, w.graph, 0));
@@ -759,12 +827,17 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
         bytes = c->shits_cap * sizeof(HitRec);
         if ((r = grow_pool(c, (void **)&c->d_shits, &bytes, nans * sizeof(HitRec)))) { c->shits_cap = 0; return r; }
         c->shits_cap = bytes / sizeof(HitRec);
+        const uint32_t mw = (uint32_t)(h.n_lights + 1 + 31) / 32;
+        if ((r = grow_pool(c, (void **)&c->d_hgeo, &c->hgeo_bytes, (size_t)gen_cap * 2 * np * sizeof(double)))) return r;
+        if ((r = grow_pool(c, (void **)&c->d_qmask, &c->qmask_bytes, (size_t)gen_cap * mw * sizeof(uint32_t)))) return r;
 
         WaveArgs a;
         memset(&a, 0, sizeof a);
         a.cap = (int)cap; a.gen_cap = gen_cap; a.scap = (int)scap;
-        a.rec = c->d_rec; a.rays = c->d_rays; a.hits = c->d_hits;
-        a.srays = c->d_srays; a.shits = c->d_shits;
+        a.rec = (double2 *)c->d_rec; a.rays = (double2 *)c->d_rays; a.hits = (double2 *)c->d_hits;
+        a.srays = (double2 *)c->d_srays; a.shits = (double2 *)c->d_shits;
+        a.hgeo = (double2 *)c->d_hgeo; a.qmask = c->d_qmask; a.mw = mw;
+        a.nl_eff = (uint32_t)(h.n_lights > 0 ? h.n_lights : 1);
         a.st = c->d_state; a.stats = c->d_stats;
         a.mb_bits = c->d_mb; a.mb_stride = (uint32_t)(full_grid * BLOCK);
         a.mb_words = mb_words; a.mb_shift = mb_shift;
@@ -814,7 +887,11 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
             do {
                 ops->trace(0, full_grid, st, c->sc, a);
                 ops->shade(0, shade_grid, st, c->sc, a);
-                if (n_sh > 0) ops->trace(1, full_grid, st, c->sc, a);
+                if (n_sh > 0) {
+                    ops->trace(1, full_grid, st, c->sc, a);
+                    ops->light(light_grid(c), st, c->sc, a);
+                    k_libm<<<libm_grid(c), 256, 0, st>>>(a, h.specular, np);
+                }
                 ops->shade(1, shade_grid, st, c->sc, a);
                 k_next_gen<<<1, 32, 0, st>>>(c->d_state, a.cap, a.gen_cap, nohandle, 0);
                 CK(cudaGetLastError());
@@ -824,10 +901,10 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
             k_pre_resolve<<<1, 32, 0, st>>>(c->d_state, nohandle, 0);
             const int ngen = hs->fail ? 0 : hs->ngen;
             for (int g = ngen - 1; g >= 1; --g) {
-                k_resolve_dev<<<c->sm_count * 4, 256, 0, st>>>(c->d_rec, c->d_state, h.specular);
+                k_resolve_dev<<<c->sm_count * 4, 256, 0, st>>>(a.rec, a.cap, c->d_state, h.specular);
                 k_resolve_next<<<1, 32, 0, st>>>(c->d_state, nohandle, 0);
             }
-            k_finish_dev<<<c->sm_count * 8, 256, 0, st>>>(c->d_rec, c->d_state, h.specular, c->d_stats);
+            k_finish_dev<<<c->sm_count * 8, 256, 0, st>>>(a.rec, a.cap, c->d_state, h.specular, c->d_stats);
             CK(cudaGetLastError());
         }
         CK(cudaMemcpyAsync(c->h_snap + (size_t)c->n_snap * WAVE_HEAD_BYTES, c->d_state, WAVE_HEAD_BYTES,
@@ -925,8 +1002,8 @@ extern "C" int ndt_b200_sync(ndt_b200_ctx *c)
             if (hs->cont) return ndt_set_error(NDT_B200_E_CUDA, "the generation loop did not finish");
             c->last.rays_bounce += (uint64_t)(hs->tail - hs->n0);
             if ((uint32_t)hs->ngen > c->last.generations) c->last.generations = (uint32_t)hs->ngen;
-            /* k_begin, 4 or 5 kernels per batch, k_pre_resolve, 2 per folded generation, k_finish */
-            c->last.launches += 1 + (uint64_t)hs->iters * (c->n_sh_pending > 0 ? 5 : 4) + 1 +
+            /* k_begin, 4 or 7 kernels per batch, k_pre_resolve, 2 per folded generation, k_finish */
+            c->last.launches += 1 + (uint64_t)hs->iters * (c->n_sh_pending > 0 ? 7 : 4) + 1 +
                                 2 * (uint64_t)(hs->ngen > 1 ? hs->ngen - 1 : 0) + 1;
         }
         if (passes == 2) c->last.launches += 1;      /* k_anaglyph */

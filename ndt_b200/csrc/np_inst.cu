@@ -70,6 +70,9 @@ int shade_grid(int sm_count, int gen_cap)
 #endif
 }
 
+const void *light_fn() { return (const void *)k_light<NP>; }
+void light(int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a) { k_light<NP><<<blocks, BLOCK, 0, st>>>(sc, a); }
+
 void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out)
 {
     k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out, (BoxRec<NP> *)box_out);
@@ -88,4 +91,4 @@ void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const 
 }  // namespace
 
 extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { trace_blocks_per_sm, trace, shade, blocks_per_sm, generation, pack_leaf, trace_rays,
-                                                     trace_fn, shade_fn, trace_smem, shade_grid };
+                                                     trace_fn, shade_fn, trace_smem, shade_grid, light_fn, light };

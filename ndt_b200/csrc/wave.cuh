@@ -155,6 +155,78 @@ NDT_FN bool shade_setup(const Scene &sc, Shade<NP> &S, int it, const double *src
     return true;
 }
 
+/* ---- the lit part of apply_lights (ndt.c:212-310), cut where the wavefront cuts it ------------------------
+ * light_geom   everything that needs N-vectors: is the shaded point the one the light sees (ndt.c:217-228,
+ *              241-249), the argument of vectNd_angle's acos (vectNd.c:64-81) and the specular dot product
+ *              (ndt.c:287-299).  `ro` / `rv` are the shadow query (origin = the light for POINT / SPOT),
+ *              `light_vec` the unit vector from the light to the point for POINT / SPOT (it is overwritten with
+ *              the light's direction for DIRECTIONAL, ndt.c:252).
+ * light_libm   the scalar tail: acos, cos, pow (ndt.c:261-268, 300) -- no vectors, a few registers
+ * light_apply  the colour update in the reference's order (ndt.c:269-273, 302-305) */
+template <int NP, bool CNT>
+NDT_FN bool light_geom(const Scene &sc, const ndt_flat_light *L, int ltype, int oid, const double *Hp, const double *Hn,
+                       const double *ro, const double *rv, double *light_vec, const Hit &T, const double *look,
+                       double &q, int &qok, double &rvdot, Tally<CNT> &tally)
+{
+    const int n = sc.n;
+    double lhn[NP];     /* light_hit_normal */
+    if (ltype == NDT_L_DIRECTIONAL) {
+        if (T.found) return false;
+        vload<NP>(light_vec, sc.geom + NDT_LDG(&L->vec_off) + NP);   /* ndt.c:252 */
+        vcopy<NP>(lhn, Hn);
+    } else {
+        if (!T.found || T.id != oid) return false;
+        double lhp[NP];
+        materialise<NP>(sc, T.win, ro, rv, lhp, lhn);
+        double dist = vdist<NP>(Hp, lhp);
+        tally.add(3 * n);
+        if (dist > EPS) return false;
+    }
+    {   /* vectNd_angle(Hn, light_vec) up to its acos (vectNd.c:64-81) */
+        double dp = vdot<NP>(Hn, light_vec);
+        double div = vnorm<NP>(Hn) * vnorm<NP>(light_vec);
+        qok = fabs(div) > EPS;
+        q = qok ? dp / div : 0.0;
+    }
+    rvdot = 0.0;
+    if (sc.specular) {                                           /* ndt.c:277-299 */
+        double lref[NP], rev_look[NP];
+        vreflect<NP>(light_vec, lhn, lref, 0.5);
+        vunit<NP>(lref);
+        vscale<NP>(look, -1, rev_look);
+        vunit<NP>(rev_look);
+        double rv_ = vdot<NP>(lref, rev_look);
+        rvdot = ref_max(0, rv_);
+    }
+    return true;
+}
+
+NDT_FN void light_libm(double q, int qok, double ldist2, double rvdot, int specular, double &light_scale, double &rvn)
+{
+    double angle = qok ? acos(q) : -1;
+    if (angle > PI / 2.0) angle = PI - angle;
+    light_scale = cos(angle) / ldist2;
+    rvn = specular ? pow(rvdot, 50) : 0.0;
+}
+
+template <int NP> struct Shade;
+template <int NP>
+NDT_FN void light_apply(const Scene &sc, Shade<NP> &S, const ndt_flat_light *L, double light_scale, double rvn)
+{
+    const double lr = NDT_LDG(&L->rgb[0]), lg = NDT_LDG(&L->rgb[1]), lb = NDT_LDG(&L->rgb[2]);
+    if (!S.transparent) {
+        S.clr0 += S.hr * lr * light_scale;
+        S.clr1 += S.hg * lg * light_scale;
+        S.clr2 += S.hb * lb * light_scale;
+    }
+    if (sc.specular) {                                           /* ndt.c:300-310 */
+        double ml = NDT_LDG(&L->max_rgb);
+        S.clr0 += S.rr * lr / ml * rvn;
+        S.clr1 += S.rg * lg / ml * rvn;
+        S.clr2 += S.rb * lb / ml * rvn;
+    }
+}
+
 /* the answer T to the query of iteration `it` */
 template <int NP, bool CNT>
 NDT_FN void shade_after(const Scene &sc, Shade<NP> &S, int it, const Hit &T, const double *src, const double *look,
@@ -186,46 +258,16 @@ NDT_FN void shade_after(const Scene &sc, Shade<NP> &S, int it, const Hit &T, con
         return;
     }
 
-    /* a shadow ray came back: ndt.c:212-310 */
-    const ndt_flat_light *L = S.L;
-    double lhn[NP];     /* light_hit_normal */
-    if (S.ltype == NDT_L_DIRECTIONAL) {
-        if (T.found) return;
-        vload<NP>(S.light_vec, sc.geom + NDT_LDG(&L->vec_off) + NP);   /* ndt.c:252 */
-        vcopy<NP>(lhn, S.Hn);
-    } else {
-        if (!T.found || T.id != S.oid) return;
-        double lhp[NP];
-        materialise<NP>(sc, T.win, S.ro, S.rv, lhp, lhn);
-        double dist = vdist<NP>(S.Hp, lhp);
-        tally.add(3 * n);
-        if (dist > EPS) return;
-    }
-    const double lr = NDT_LDG(&L->rgb[0]), lg = NDT_LDG(&L->rgb[1]), lb = NDT_LDG(&L->rgb[2]);
-    double angle = vangle<NP>(S.Hn, S.light_vec);
-    if (angle > PI / 2.0) angle = PI - angle;
-    double light_scale = cos(angle) / S.ldist2;
+    /* a shadow ray came back: ndt.c:212-310, in three steps that the wavefront runs as separate kernels
+     * (light_geom per shadow query, light_libm per shadow query at full occupancy, light_apply per ray) */
+    double q, ldist2 = S.ldist2, rvdot;
+    int qok;
+    if (!light_geom<NP, CNT>(sc, S.L, S.ltype, S.oid, S.Hp, S.Hn, S.ro, S.rv, S.light_vec, T, look, q, qok, rvdot, tally)) return;
+    double light_scale, rvn;
+    light_libm(q, qok, ldist2, rvdot, sc.specular, light_scale, rvn);
+    light_apply<NP>(sc, S, S.L, light_scale, rvn);
     tally.add(6 * n + 8);
-    if (!S.transparent) {
-        S.clr0 += S.hr * lr * light_scale;
-        S.clr1 += S.hg * lg * light_scale;
-        S.clr2 += S.hb * lb * light_scale;
-    }
-    if (sc.specular) {                                           /* ndt.c:277-310 */
-        double lref[NP], rev_look[NP];
-        vreflect<NP>(S.light_vec, lhn, lref, 0.5);
-        vunit<NP>(lref);
-        vscale<NP>(look, -1, rev_look);
-        vunit<NP>(rev_look);
-        double rv_ = vdot<NP>(lref, rev_look);
-        rv_ = ref_max(0, rv_);
-        double rvn = pow(rv_, 50);
-        double ml = NDT_LDG(&L->max_rgb);
-        S.clr0 += S.rr * lr / ml * rvn;
-        S.clr1 += S.rg * lg / ml * rvn;
-        S.clr2 += S.rb * lb / ml * rvn;
-        tally.add(16 * n + 14);
-    }
+    if (sc.specular) tally.add(16 * n + 14);
 }
 
 /* the record of the ray and the rays it spawns */
