@@ -535,34 +535,43 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
     int kd_overflow = 0;
     int *next = MODE ? &st->next1 : &st->next0;
 
-    while (true) {
+#ifndef NDT_TRACE_DRAW
+#define NDT_TRACE_DRAW 1     /* 32-ray bundles per draw of the work counter: 4 measured 7-10 % slower (the heavy bundles of a silhouette end up in one warp) */
+#endif
+    bool stop = false;
+    while (!stop) {
         /* (fetching the counter one batch ahead was measured slower: profiles/r01_experiments.md) */
-        int base = 0;
-        if (lane == 0) base = atomicAdd(next, 32);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= count) break;
-        const int r = base + lane;
-        double o[NP], v[NP], limit = -1.0;
-        bool want;
-        int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
-        int dest = 0;                /* MODE 1: index of the answer in shits[] */
-        if (MODE == 0) {
-            double frac; int depth, tx, ty;
-            want = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
-        } else {
-            want = r < count;
-            if (want) {
-                int code;
-                ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)r, o, v, limit, code, dest);
-                dir_light = code - 1;
+        int base0 = 0;
+        if (lane == 0) base0 = atomicAdd(next, 32 * NDT_TRACE_DRAW);
+        base0 = __shfl_sync(FULL, base0, 0);
+        if (base0 >= count) break;
+        NDT_NO_UNROLL
+        for (int kk = 0; kk < NDT_TRACE_DRAW; ++kk) {
+            const int base = base0 + 32 * kk;
+            if (base >= count) break;
+            const int r = base + lane;
+            double o[NP], v[NP], limit = -1.0;
+            bool want;
+            int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
+            int dest = 0;                /* MODE 1: index of the answer in shits[] */
+            if (MODE == 0) {
+                double frac; int depth, tx, ty;
+                want = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+            } else {
+                want = r < count;
+                if (want) {
+                    int code;
+                    ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)r, o, v, limit, code, dest);
+                    dir_light = code - 1;
+                }
             }
-        }
-        Hit T;
-        trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
-        if (ws.fault) break;     /* warp-uniform (warp.cuh) */
-        if (want) {
-            if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), T.t, T.id, T.win, T.found);
-            else hit_store_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, T.t, T.id, T.win, T.found);
+            Hit T;
+            trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
+            if (ws.fault) { stop = true; break; }     /* warp-uniform (warp.cuh) */
+            if (want) {
+                if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), T.t, T.id, T.win, T.found);
+                else hit_store_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, T.t, T.id, T.win, T.found);
+            }
         }
     }
     if (kd_overflow) atomicMax(&st->kd_fault, 1);
