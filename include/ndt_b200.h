@@ -162,8 +162,13 @@ int ndt_b200_render_aa(ndt_b200_ctx *ctx, int aa_diff, int aa_depth,
  * (1).  `kdtree` is the extra argument: the reference reads its global
  * (ndt.c:68), a library cannot.  Supports what the device path supports:
  * samples == 1, every stereo mode and camera type, recursive_aa off; anything
- * else returns a negative status instead of rendering.  When img_copy is non-NULL it
- * receives the fp64 frame exactly like ndt.c:1024-1027. */
+ * else returns a negative status instead of rendering.  img_copy receives the fp64
+ * frame when name and img_copy are non-NULL, depth_copy the depth map when depth_name
+ * and depth_copy are (ndt.c:1024-1031: image_copy, which initialises the destination
+ * without freeing it); writing the image FILES is the binding's job -- the codecs stay
+ * on the host.  cam.dirX is rescaled in place like ndt.c:925-926 once
+ * the frame has been rendered.  Environment: NDT_B200_DEVICES=<n>|all renders the frame
+ * on that many GPUs of the box (ndt_b200_mgpu_render_frame); default 1. */
 int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_b200_host_api *host,
                           char *name, char *depth_name, int width, int height,
                           int samples, int stereo_mode, int threads, int aa_diff,
@@ -178,6 +183,32 @@ int ndt_b200_render_image_aa(void *scene, const void *kdtree, const ndt_b200_hos
                              int samples, int stereo_mode, int threads, int aa_diff,
                              int aa_depth, int max_optic_depth, int specular,
                              void *img_copy, void *depth_copy);
+
+/* ---- all GPUs of one box (mgpu.cu) ------------------------------------------
+ * Replaces the MPI layer of the reference for one node: rows of a frame (ndt.c:812-820) and frames of an
+ * animation (ndt.c:1771-1787) are spread over the GPUs, results land in the caller's host buffers -- what
+ * mpi_collect_image (ndt.c:1277-1309) does for rank 0.  One host thread per context, two contexts per GPU,
+ * work items pulled from one atomic counter (dynamic queue); no collective on the data path.
+ * n_devices <= 0: every visible GPU; devices == NULL: 0 .. n_devices-1. */
+typedef struct ndt_b200_mgpu ndt_b200_mgpu;
+int ndt_b200_mgpu_init(int n_devices, const int *devices, ndt_b200_mgpu **out);
+void ndt_b200_mgpu_destroy(ndt_b200_mgpu *m);
+int ndt_b200_mgpu_devices(const ndt_b200_mgpu *m);
+/* ONE frame as row bands of band_rows rows (<= 0: about four bands per context): every context uploads the scene
+ * and pulls bands until none is left; each band is copied from its GPU into the rows it covers of the HOST
+ * buffers (layout and meaning as ndt_b200_render_tile for the whole frame; any may be NULL).  Byte-identical to
+ * the one-GPU render of the same frame: a pixel does not depend on which tile it is in. */
+int ndt_b200_mgpu_render_frame(ndt_b200_mgpu *m, const ndt_flat_scene *fs, int band_rows,
+                               double *rgba_f64, uint8_t *rgba_u8, uint8_t *hit, int32_t *obj_id,
+                               double *inv_depth, ndt_b200_stats *stats);
+/* An ANIMATION, frame by frame: the scene is copied, the call returns as soon as the frame is queued (it blocks
+ * while 2 x contexts frames are already waiting), whichever context is free uploads and renders it into the HOST
+ * buffers (either may be NULL), which must stay valid until ndt_b200_mgpu_wait.  This is how a stateful scene
+ * (scenes/balls.c: scene_setup must run for every frame in order, ndt.c:1816-1825) keeps all GPUs busy: the
+ * host produces flat scenes sequentially, the frames render concurrently. */
+int ndt_b200_mgpu_submit(ndt_b200_mgpu *m, const ndt_flat_scene *fs, uint8_t *rgba_u8, double *rgba_f64);
+/* all submitted frames are in their buffers; statistics summed over them; the first failure, if any */
+int ndt_b200_mgpu_wait(ndt_b200_mgpu *m, ndt_b200_stats *stats);
 
 /* Page-locked host memory (cudaMallocHost) for render_tile outputs and flat
  * scenes; plain malloc'ed buffers work too, only slower to copy. */

