@@ -76,3 +76,49 @@ def gather_tiles(dist, rank, world, items, mine, stage, frames, band):
         for k in range(t[0]):
             owners[t[1 + k]] = r
     return owners
+
+
+class FrameGather:
+    """Finished frames -> rank 0, each sent as soon as it is rendered, while the next one renders.
+
+    Every rank renders `frames_per_rank` frames per step (global frame f = rank * frames_per_rank + j).  Rank 0
+    posts the receives of a whole step up front, one grouped NCCL operation per round j (world - 1 receives
+    straight into the destination frames); rank k issues send j when its frame j is done -- frames finish out of
+    order with two contexts per GPU, the sends go out in order j = 0, 1, ... because NCCL matches the operations
+    of a pair by their order.  Nothing here waits for the GPU except end().  This is the overlapped form of the
+    reference's mpi_collect_image (ndt.c:1277-1309); backend-agnostic (gloo in the CPU tests)."""
+
+    def __init__(self, dist, rank, world, frames_per_rank):
+        self.dist, self.rank, self.world, self.F = dist, rank, world, frames_per_rank
+        self.reqs = []
+        self.ready = {}
+        self.next_j = 0
+
+    def begin(self, frames):
+        """frames: [world * F, ...] on rank 0 (None elsewhere)"""
+        d = self.dist
+        self.reqs, self.ready, self.next_j = [], {}, 0
+        if self.rank == 0:
+            for j in range(self.F):
+                ops = [d.P2POp(d.irecv, frames[k * self.F + j], k) for k in range(1, self.world)]
+                if ops:
+                    self.reqs += d.batch_isend_irecv(ops)
+
+    def send(self, tensor, j):
+        """rank != 0: frame j of this step is complete in `tensor`"""
+        d = self.dist
+        self.ready[j] = tensor
+        while self.next_j in self.ready:
+            t = self.ready.pop(self.next_j)
+            self.reqs += d.batch_isend_irecv([d.P2POp(d.isend, t, 0)])
+            self.next_j += 1
+
+    def end(self):
+        assert self.rank == 0 or self.next_j == self.F, "a frame of this step was never handed to send()"
+        cuda = False
+        for r in self.reqs:
+            r.wait()
+            cuda = True
+        self.reqs = []
+        if cuda and torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()

@@ -78,3 +78,40 @@ def test_single_rank_queue_is_a_plain_range():
     from ndt_b200 import multi
     q = multi.TileQueue(None, 0, 1)
     assert list(q.pull(0, 7)) == list(range(7))
+
+
+def _gather_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from ndt_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    F, shape = 3, (5, 7, 4)
+    g = multi.FrameGather(dist, rank, world, F)
+    frames = torch.zeros((world * F,) + shape, dtype=torch.uint8) if rank == 0 else None
+    for step in range(3):
+        g.begin(frames)
+        mine = [torch.full(shape, 10 * step + rank * F + j, dtype=torch.uint8) for j in range(F)]
+        for j in (1, 0, 2):                 # frames finish out of order (two contexts per GPU); sends go out in order
+            if rank == 0:
+                frames[j] = mine[j]
+            else:
+                g.send(mine[j], j)
+        g.end()
+        if rank == 0:
+            for f in range(world * F):
+                assert int(frames[f].min()) == int(frames[f].max()) == 10 * step + f, (step, f)
+    if rank == 0:
+        np.save(out_path, frames.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frames_are_sent_as_they_finish_and_land_in_order(tmp_path):
+    """FrameGather (bench.py's N>1 gather): rank 0 posts a step's receives up front, the other rank sends frame j
+    when it is done -- whatever order the frames finish in, frame f ends up in slot f."""
+    out = str(tmp_path / "g.npy")
+    mp.spawn(_gather_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    frames = np.load(out)
+    assert [int(frames[f, 0, 0, 0]) for f in range(6)] == [20 + f for f in range(6)]

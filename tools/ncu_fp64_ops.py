@@ -50,6 +50,9 @@ def main():
         a["pipe_pct_wsum"] += d.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * t
         a["t_raw"] += t
         a["regs"] = max(a["regs"], d.get("launch__registers_per_thread", 0))
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            u2 = d.get("unit:" + m, "byte")
+            a["dram"] += d.get(m, 0.0) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u2, 1.0)
     tot_ms = sum(a["ms"] for a in agg.values())
     print(f"{'kernel':28s} {'n':>4s} {'ms':>8s} {'share':>6s} {'DADD+DMUL+DFMA (G thread-inst)':>32s} {'Ginst/s':>9s} {'pipe%':>6s} {'regs':>5s}")
     res = {"frame_kernel_ms_under_ncu": tot_ms, "kernels": {}}
@@ -59,9 +62,13 @@ def main():
         print(f"{nm:28s} {a['launches']:4d} {a['ms']:8.3f} {a['ms']/tot_ms*100:5.1f}% {ops/1e9:32.3f} {ops/1e9/(a['ms']*1e-3) if a['ms'] else 0:9.1f} {pipe:6.1f} {int(a['regs']):5d}")
         res["kernels"][nm] = {"launches": a["launches"], "ms_under_ncu": a["ms"], "dadd": a["dadd"], "dmul": a["dmul"],
                               "dfma": a["dfma"], "fp64_thread_inst": a["fp64_thread_inst"], "fp64_warp_inst": a["fp64_warp_inst"],
-                              "warp_inst": a["warp_inst"], "fp64_pipe_active_pct": pipe, "registers": int(a["regs"])}
+                              "warp_inst": a["warp_inst"], "fp64_pipe_active_pct": pipe, "registers": int(a["regs"]),
+                              "dram_bytes": a["dram"]}
     allops = sum(k["dadd"] + k["dmul"] + k["dfma"] for k in res["kernels"].values())
     res["fp64_thread_inst_dadd_dmul_dfma"] = allops
+    res["dram_bytes_k_trace"] = sum(k["dram_bytes"] for n_, k in res["kernels"].items() if "k_trace" in n_) or None
+    res["source"] = "ncu --metrics gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum,... " \
+                    "--clock-control none on `NDT_B200_NO_GRAPH=1 python tools/perf_frame.py <workload> 1` (second frame); " + path
     print(f"{'frame':28s} {'':4s} {tot_ms:8.3f} {'':6s} {allops/1e9:32.3f}")
     if out:
         json.dump(res, open(out, "w"), indent=1)

@@ -9,7 +9,7 @@ import bench
 wl = sys.argv[1] if len(sys.argv) > 1 else "config2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 key, W, H, *_ = bench.WORKLOADS[wl]
-flat = bench.load_flat(key, W, H)
+flat = bench.load_flats(wl)[int(os.environ.get('NDT_FRAME', '0'))]
 ctx = ndt_b200.Context(0)
 ctx.upload(flat)
 if os.environ.get('NDT_OPTS'):
