@@ -309,6 +309,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # the frames go out over NVLink in the background of the render: two channels per peer carry the 8-33 MB of a
+        # frame in a fraction of its render time and leave the SMs to the persistent trace kernels
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
@@ -331,9 +334,11 @@ def run_ours(args, rank, world, local_rank):
     frames_dev = [torch.zeros((n_frames, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if rank == 0 else None
     stage = [torch.zeros((F, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(nbuf)] if rank != 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    gather = multi.FrameGather(dist, rank, world, F) if world > 1 else None
+    gathers = [multi.FrameGather(dist, rank, world, F) for _ in range(nbuf)] if world > 1 else None
 
     def barrier():
+        for g in (gathers or []):
+            g.end()                 # every frame of every step has arrived
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -341,9 +346,10 @@ def run_ours(args, rank, world, local_rank):
     totals = {"rays": 0, "dev_ms": 0.0, "launches": 0, "h2d": 0}
     lock = threading.Lock()
 
-    def run_frames(work_one):
+    def run_frames(work_one, after_start=None):
         """work_one(ctx, j) for my frames j = 0..F-1 on IN_FLIGHT host threads (ctypes releases the GIL inside the
-        library); yields j as frames finish, in completion order."""
+        library); yields j as frames finish, in completion order.  after_start() runs in the calling thread once
+        the workers are rendering."""
         todo = list(range(F))
         done = queue.Queue()
 
@@ -362,6 +368,8 @@ def run_ours(args, rank, world, local_rank):
         ths = [threading.Thread(target=body, args=(c,)) for c in ctxs]
         for t in ths:
             t.start()
+        if after_start is not None:
+            after_start()
         live = len(ths)
         try:
             while live:
@@ -388,8 +396,13 @@ def run_ours(args, rank, world, local_rank):
         b = i % nbuf
         flush.fill_(i & 0xFF)                                     # L2 flush between steps
         torch.cuda.current_stream().synchronize()
-        if gather is not None:
-            gather.begin(frames_dev[b] if rank == 0 else None)   # rank 0: the receives of this step, posted up front
+        g = gathers[b] if gathers else None
+        if g is not None:
+            g.end()                 # the transfers of the step that used this buffer last (two steps ago) are complete
+
+        def post():                 # rank 0: the receives of this step, posted while its own frames already render
+            if g is not None:
+                g.begin(frames_dev[b] if rank == 0 else None)
 
         def one(c, j):
             f = mine[j]
@@ -401,11 +414,9 @@ def run_ours(args, rank, world, local_rank):
                 totals["rays"] += st.rays_unique
                 totals["dev_ms"] += st.device_ms
                 totals["launches"] += st.launches
-        for j in run_frames(one):
-            if gather is not None and rank != 0:
-                gather.send(stage[b][j], j)                       # NCCL, while the next frame renders
-        if gather is not None:
-            gather.end()                                          # sends / receives of this step are complete
+        for j in run_frames(one, post):
+            if g is not None and rank != 0:
+                g.send(stage[b][j], j)                            # NCCL, while the next frame renders
 
     def timed(fn, k, w):
         for i in range(w):

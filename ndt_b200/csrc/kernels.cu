@@ -363,6 +363,9 @@ struct ndt_b200_ctx {
     HitRec *d_hits; size_t hits_cap;     /* one per record slot */
     char *d_srays; size_t srays_bytes;   /* shadow queries of one batch */
     HitRec *d_shits; size_t shits_cap;
+    /* recursive anti-aliasing scratch (ndt_b200_render_aa): grown on demand, kept for the next frame */
+    struct { void *p; size_t bytes; } aa_img, aa_fin, aa_u8, aa_samp, aa_xy[2], aa_cells[64];
+    int *d_aa_cnt; unsigned long long *d_aa_res;
     double *d_hgeo; size_t hgeo_bytes;   /* hit point + normal per ray of a batch */
     uint32_t *d_qmask; size_t qmask_bytes;
     int trace_grid[2][8];                /* cached k_trace occupancy per (boxed scene, NP/2) */
@@ -460,6 +463,9 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
     cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_hgeo); cudaFree(c->d_qmask);
+    cudaFree(c->aa_img.p); cudaFree(c->aa_fin.p); cudaFree(c->aa_u8.p); cudaFree(c->aa_samp.p);
+    cudaFree(c->aa_xy[0].p); cudaFree(c->aa_xy[1].p); cudaFree(c->d_aa_cnt); cudaFree(c->d_aa_res);
+    for (int l = 0; l < 64; ++l) cudaFree(c->aa_cells[l].p);
     cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_out); cudaFree(c->d_state);
     cudaFreeHost(c->h_ctr); cudaFreeHost(c->h_stats); cudaFreeHost(c->h_snap);
     if (c->wg.exec) cudaGraphExecDestroy(c->wg.exec);
@@ -1412,6 +1418,9 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
     ndt_b200_stats acc;
     memset(&acc, 0, sizeof acc);
     int r = 0;
+    /* every buffer of the pass lives in the context and only ever grows: an animation rendered with -a allocates
+     * during its first frames and then never again (the per-level cudaMalloc / cudaFree of round 1 cost a device
+     * synchronisation each) */
     double *d_img = NULL, *d_fin = NULL;
     uint8_t *d_u8 = NULL;
     int *d_cnt = NULL;
@@ -1419,14 +1428,17 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
     AaCell *lvl_cells[64];
     int lvl_n[64], nlvl = 0;
     double *d_xy = NULL, *d_samp = NULL;
+    int xy_cur = 0;
     memset(lvl_cells, 0, sizeof lvl_cells);
 #define AA_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
         r = ndt_set_error(NDT_B200_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); goto aa_done; } } while (0)
-    AA_CK(cudaMalloc(&d_img, gpx * 32));
-    AA_CK(cudaMalloc(&d_fin, px * 32));
-    AA_CK(cudaMalloc(&d_u8, px * 4));
-    AA_CK(cudaMalloc(&d_cnt, sizeof(int)));
-    AA_CK(cudaMalloc(&d_res, sizeof(unsigned long long)));
+#define AA_GROW(slot, want) do { if ((r = grow_pool(c, &(slot).p, &(slot).bytes, (want)))) goto aa_done; } while (0)
+    AA_GROW(c->aa_img, gpx * 32); d_img = (double *)c->aa_img.p;
+    AA_GROW(c->aa_fin, px * 32); d_fin = (double *)c->aa_fin.p;
+    AA_GROW(c->aa_u8, px * 4); d_u8 = (uint8_t *)c->aa_u8.p;
+    if (!c->d_aa_cnt) AA_CK(cudaMalloc(&c->d_aa_cnt, sizeof(int)));
+    if (!c->d_aa_res) AA_CK(cudaMalloc(&c->d_aa_res, sizeof(unsigned long long)));
+    d_cnt = c->d_aa_cnt; d_res = c->d_aa_res;
     AA_CK(cudaMemsetAsync(d_res, 0, sizeof(unsigned long long), st));
 
     /* the initial image: one sample per corner (render_lines_thread with width+1, height+1) */
@@ -1450,8 +1462,8 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
     } else {
         const double thr = aa_diff / 255.0;
         double step = 1.0;
-        AA_CK(cudaMalloc(&lvl_cells[0], (px ? px : 1) * sizeof(AaCell)));
-        AA_CK(cudaMalloc(&d_xy, (px ? px : 1) * 10 * sizeof(double)));
+        AA_GROW(c->aa_cells[0], (px ? px : 1) * sizeof(AaCell)); lvl_cells[0] = (AaCell *)c->aa_cells[0].p;
+        AA_GROW(c->aa_xy[0], (px ? px : 1) * 10 * sizeof(double)); d_xy = (double *)c->aa_xy[0].p;
         AA_CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
         k_aa_level0<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(d_img, W, H, thr, !aa_terminal(aa_depth, step), d_fin,
                                                                  lvl_cells[0], d_cnt, d_xy, d_res);
@@ -1464,14 +1476,13 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
             lvl_n[nlvl] = n;
             if ((size_t)n * 5 > 0x3ffffff0u) { r = ndt_set_error(NDT_B200_E_OVERFLOW, "too many anti-aliasing samples in one level"); goto aa_done; }
             /* this level's samples: one wavefront over the list */
-            cudaFree(d_samp); d_samp = NULL;
-            AA_CK(cudaMalloc(&d_samp, (size_t)n * 5 * 32));
+            AA_GROW(c->aa_samp, (size_t)n * 5 * 32); d_samp = (double *)c->aa_samp.p;
             if ((r = aa_render_samples(c, d_xy, n * 5, d_samp, &acc, 0))) goto aa_done;
             const int next_terminal = aa_terminal(aa_depth, step / 2);
             double *d_xy_next = NULL;
             if (!next_terminal) {
-                AA_CK(cudaMalloc(&lvl_cells[nlvl + 1], (size_t)n * 4 * sizeof(AaCell)));
-                AA_CK(cudaMalloc(&d_xy_next, (size_t)n * 4 * 10 * sizeof(double)));
+                AA_GROW(c->aa_cells[nlvl + 1], (size_t)n * 4 * sizeof(AaCell)); lvl_cells[nlvl + 1] = (AaCell *)c->aa_cells[nlvl + 1].p;
+                AA_GROW(c->aa_xy[xy_cur ^ 1], (size_t)n * 4 * 10 * sizeof(double)); d_xy_next = (double *)c->aa_xy[xy_cur ^ 1].p;
             }
             AA_CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
             k_aa_subdivide<<<(n + 127) / 128, 128, 0, st>>>(lvl_cells[nlvl], n, d_samp, thr, next_terminal,
@@ -1480,7 +1491,7 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
             int nn = 0;
             AA_CK(cudaMemcpyAsync(&nn, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
             AA_CK(cudaStreamSynchronize(st));
-            cudaFree(d_xy); d_xy = d_xy_next;
+            d_xy = d_xy_next; xy_cur ^= 1;
             ++nlvl;
             step /= 2;
             n = nn;
@@ -1503,10 +1514,8 @@ extern "C" int ndt_b200_render_aa(ndt_b200_ctx *c, int aa_diff, int aa_depth,
     if (stats) *stats = acc;
 aa_done:
 #undef AA_CK
+#undef AA_GROW
     cudaStreamSynchronize(st);
-    cudaFree(d_img); cudaFree(d_fin); cudaFree(d_u8); cudaFree(d_cnt); cudaFree(d_res);
-    cudaFree(d_xy); cudaFree(d_samp);
-    for (int l = 0; l < 64; ++l) cudaFree(lvl_cells[l]);
     return r;
 }
 

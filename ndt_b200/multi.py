@@ -114,11 +114,13 @@ class FrameGather:
             self.next_j += 1
 
     def end(self):
+        if not self.reqs and not self.ready and self.next_j == 0:
+            return                  # nothing begun
         assert self.rank == 0 or self.next_j == self.F, "a frame of this step was never handed to send()"
         cuda = False
         for r in self.reqs:
             r.wait()
             cuda = True
-        self.reqs = []
+        self.reqs, self.next_j = [], 0
         if cuda and torch.cuda.is_available():
             torch.cuda.current_stream().synchronize()

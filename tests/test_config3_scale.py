@@ -13,7 +13,6 @@ import pytest
 import ndt_b200
 
 pytestmark = pytest.mark.gpu
-N_OBJECTS = 1500
 W, H = 160, 90
 
 
@@ -36,8 +35,14 @@ def primary_rays(flat, step):
     return np.array(rays_o), np.array(rays_v), pix
 
 
-@pytest.mark.parametrize("growth", [1.5, 1.95])
-def test_random_scene_with_a_bounded_tree_against_brute_force(ref, growth):
+# (objects, max_growth, pixel step of the sub-sampled grid, extra rays aimed at objects).  The last row is BASELINE
+# config 3 as stated -- ~10 k objects: a tree the reference cannot build (SURVEY note 8); its own trace_kd walking
+# the bounded tree is the expected answer, ray for ray
+CONFIG3_CASES = [(1500, 1.5, 3, 1500), (1500, 1.95, 3, 1500), (10000, 1.95, 9, 700)]
+
+
+@pytest.mark.parametrize("N_OBJECTS,growth,step,n_extra", CONFIG3_CASES, ids=["n1500_g1.5", "n1500_g1.95", "n10000_g1.95"])
+def test_random_scene_with_a_bounded_tree_against_brute_force(ref, N_OBJECTS, growth, step, n_extra):
     ref.open_scene("random")
     t0 = time.perf_counter()
     ref.begin_frame_nokd(6, 0, 300, str(N_OBJECTS))
@@ -50,7 +55,7 @@ def test_random_scene_with_a_bounded_tree_against_brute_force(ref, growth):
         flat = ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, W, H, 128, 1, ref.get_bounds_ptr)
         hd = flat.header
         assert hd.n_items == N_OBJECTS
-        o, v, pix = primary_rays(flat, 3)
+        o, v, pix = primary_rays(flat, step)
         n_prim = len(o)
         # the camera of random.c sees little of the cloud (its 6-D objects rarely cut the 3-D view): add rays
         # aimed at the objects, from the camera and from inside the cloud
@@ -58,7 +63,7 @@ def test_random_scene_with_a_bounded_tree_against_brute_force(ref, growth):
         bs = np.frombuffer(flat.blob, np.float64, hd.n_objects * (hd.npad + 2), hd.off_bspheres).reshape(hd.n_objects, hd.npad + 2)
         cam_pos = o[0].copy()
         eo, ev = [], []
-        for k in range(1500):
+        for k in range(n_extra):
             i = rng.integers(hd.n_items)
             src = cam_pos if k % 2 == 0 else rng.uniform(2.0, 12.0, size=hd.n)
             tgt = bs[i, :hd.n] + rng.normal(size=hd.n) * abs(bs[i, hd.npad]) * 0.4
@@ -91,4 +96,4 @@ def test_random_scene_with_a_bounded_tree_against_brute_force(ref, growth):
     # the frame's primary-ray buffers agree with the probe
     got_id = np.array([frame.obj_id[j, i] for j, i in pix])
     assert np.array_equal(got_id, oid[:n_prim])
-    assert n_hits > 500
+    assert n_hits > min(500, n_extra // 2)

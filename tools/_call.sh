@@ -1,10 +1,8 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r02_pytest16.log
-cat gpurun_out/r02_pytest16.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench16.json 2> gpurun_out/r02_bench16.err; tail -3 gpurun_out/r02_bench16.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench16_ref.json 2> gpurun_out/r02_bench16_ref.err
-M=gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__thread_inst_executed_pipe_fp64_pred_on.sum,smsp__inst_executed_pipe_fp64.sum,smsp__inst_executed.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,dram__bytes_read.sum,dram__bytes_write.sum
-export NDT_B200_NO_GRAPH=1
-for w in config2 config1 config4 config5_yaml; do
-python tools/perf_frame.py $w 1 > gpurun_out/plain_$w.log 2>&1 && ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_launches_fp64_$w.csv python tools/perf_frame.py $w 1 > gpurun_out/ncu_$w.log 2>&1
+timeout 1800 python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -25 > gpurun_out/r02_pytest21.log
+cat gpurun_out/r02_pytest21.log
+L=gpurun_out/r02_config3.log; : > $L
+for p in "1.5 16 64" "1.95 16 64" "3.0 8 128" "3.0 11 128" "3.0 14 64"; do
+  timeout 600 python tools/bench_config3.py 10000 3840 2160 $p 2>/dev/null | tail -1 >> $L
 done
+cat $L
