@@ -83,15 +83,18 @@ int render_image(void *scn, char *name, char *depth_name, int width, int height,
         FILE *f = fopen(path, "wb");
         if (f) {
             fprintf(f, "P6\n%d %d\n255\n", width, height);
-            if (img->pixel_width == 4) {         /* the anti-aliased frame is already 8-bit RGBA */
-                for (size_t i = 0; i < (size_t)width * height; ++i) fwrite(img->pixels + 4 * i, 1, 3, f);
-            } else {
-                const double *px = (const double *)img->pixels;
-                for (size_t i = 0; i < (size_t)width * height; ++i) {
-                    unsigned char rgb[3] = { d2c(px[4 * i]), d2c(px[4 * i + 1]), d2c(px[4 * i + 2]) };
-                    fwrite(rgb, 1, 3, f);
+            unsigned char *row = malloc((size_t)width * 3);
+            for (int y = 0; row && y < height; ++y) {
+                if (img->pixel_width == 4) {         /* the anti-aliased frame is already 8-bit RGBA */
+                    const unsigned char *px = img->pixels + (size_t)y * width * 4;
+                    for (int x = 0; x < width; ++x) { row[3 * x] = px[4 * x]; row[3 * x + 1] = px[4 * x + 1]; row[3 * x + 2] = px[4 * x + 2]; }
+                } else {
+                    const double *px = (const double *)img->pixels + (size_t)y * width * 4;
+                    for (int x = 0; x < width; ++x) { row[3 * x] = d2c(px[4 * x]); row[3 * x + 1] = d2c(px[4 * x + 1]); row[3 * x + 2] = d2c(px[4 * x + 2]); }
                 }
+                fwrite(row, 3, (size_t)width, f);
             }
+            free(row);
             fclose(f);
             printf("\tndt_b200: wrote %s\n", path);
         }

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "ndt_abi.h"
 #include "ndt_internal.h"
 #include "gen.cuh"
@@ -1596,12 +1597,16 @@ extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_
     if (samples != 1) return ndt_set_error(NDT_B200_E_UNSUPPORTED, "samples=%d: jittered sampling uses drand48 (ndt.c:505-542) and is not on the device path", samples);
     ndt_b200_ctx *&ctx = g_render_image_ctx;
     int r;
+    const bool timing = getenv("NDT_B200_TIMING") != NULL;     /* per-stage wall times of the call on stderr */
+    struct timespec ts0, ts1, ts2, ts3;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     const int want_devices = render_image_devices();
     if (want_devices > 1) {
         if (!g_render_image_mgpu && (r = ndt_b200_mgpu_init(want_devices, NULL, &g_render_image_mgpu))) return r;
     } else if (!ctx && (r = ndt_b200_init(0, &ctx))) return r;
     ndt_flat_scene *fs = NULL;
     if ((r = ndt_b200_flatten_view(scene, kdtree, width, height, max_optic_depth, specular, stereo_mode, host, &fs))) return r;
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
     if (want_devices <= 1) {
         r = ndt_b200_upload(ctx, fs);
         ndt_b200_free_flat(fs);
@@ -1628,6 +1633,7 @@ extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_
         r = ndt_b200_render_tile(ctx, 0, 0, width, height, f64, NULL, NULL, NULL, dep, NULL);
     }
     if (r) { free(f64); free(dep); free(dep_rgba); return r; }
+    clock_gettime(CLOCK_MONOTONIC, &ts2);
     rescale_dirx(scene, stereo_mode != NDT_HIDEF_3D ? width / (double)height : width / (double)1080);
     if (img) { give_image(img, width, height, 32, f64); f64 = NULL; }      /* fp64 RGBA, row-major */
     if (dimg) {     /* depth map: r=g=b=1/dist, a=1 (ndt.c:754-756) */
@@ -1636,5 +1642,13 @@ extern "C" int ndt_b200_render_image(void *scene, const void *kdtree, const ndt_
         dep_rgba = NULL;
     }
     free(f64); free(dep); free(dep_rgba);
+    if (timing) {
+        clock_gettime(CLOCK_MONOTONIC, &ts3);
+#define MS(a, b) (((b).tv_sec - (a).tv_sec) * 1e3 + ((b).tv_nsec - (a).tv_nsec) * 1e-6)
+        fprintf(stderr, "ndt_b200_render_image %dx%d on %d GPU(s): init + flatten %.1f ms, upload + alloc + render + read-back %.1f ms "
+                "(device %.2f ms), copy-out %.1f ms\n", width, height, want_devices, MS(ts0, ts1), MS(ts1, ts2),
+                want_devices <= 1 ? ctx->last.device_ms : 0.0, MS(ts2, ts3));
+#undef MS
+    }
     return 1;
 }

@@ -24,7 +24,8 @@ def test_odd_dimension_is_padded():
     assert f.header.n == 5 and f.header.npad == 6
 
 
-@pytest.mark.parametrize("mutate", ["truncate", "magic", "node", "leaf", "object"])
+@pytest.mark.parametrize("mutate", ["truncate", "magic", "node", "leaf", "object", "light_type", "light_vec", "geom_extent",
+                                    "node_cycle", "tree_depth", "max_leaf"])
 def test_validate_rejects_corruption(mutate):
     f = load_flat("config4_balls5d")
     b = bytearray(f.blob)
@@ -39,6 +40,20 @@ def test_validate_rejects_corruption(mutate):
         C.c_int32.from_buffer(b, h.off_leaf_refs).value = h.n_items    # id out of range
     elif mutate == "object":
         C.c_int32.from_buffer(b, h.off_objects).value = 99             # unknown type
+    elif mutate == "light_type":
+        C.c_int32.from_buffer(b, h.off_lights).value = 7               # ndt_flat_light.type outside scene.h:17-23
+    elif mutate == "light_vec":                                        # ndt_flat_light.vec_off (offset 48): 4 npad doubles must fit geom[]
+        C.c_uint32.from_buffer(b, h.off_lights + 48).value = h.n_geom - 2
+    elif mutate == "geom_extent":                                      # ndt_flat_object.geom_off (offset 24): the block must fit geom[]
+        C.c_uint32.from_buffer(b, h.off_objects + 24).value = (h.n_geom - 2) & ~1
+    elif mutate == "node_cycle":                                       # a child that is not behind its parent (pre-order)
+        C.c_int32.from_buffer(b, h.off_nodes + 4).value = 0
+    elif mutate == "tree_depth":                                       # header says shallower than the nodes are
+        hdr = ndt_b200.FlatHeader.from_buffer(b)
+        hdr.tree_depth = 1
+    elif mutate == "max_leaf":
+        hdr = ndt_b200.FlatHeader.from_buffer(b)
+        hdr.max_leaf = 1
     with pytest.raises(ndt_b200.NdtB200Error):
         ndt_b200.FlatScene(bytes(b))
 
