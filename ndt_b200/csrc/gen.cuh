@@ -89,13 +89,63 @@ struct GenArgs {
     const void *boxrec;      /* BoxRec<NP>[n_leaf_refs] */
 };
 
-/* leaf_refs[] -> LeafRec stream: one thread per reference, once per uploaded scene */
+/* The box of everything an orthotope can report as a hit (see box_hit in warp.cuh): p0 + sum s_a b_a, s_a in
+ * [-EPS, len_a + EPS], thickened by sqrt(2 EPS) = 0.0142; margins doubled.  Doubles, before the outward rounding. */
 template <int NP>
-__global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out, BoxRec<NP> *box_out)
+__device__ __forceinline__ void orthotope_reach(const Scene &sc, const ndt_flat_object *fo, double *lo_out, double *hi_out)
+{
+    const int m = fo->n_axes;
+    const double *g = sc.geom + fo->geom_off, *p0 = g, *basis = g + NP, *len = basis + (size_t)m * NP;
+    for (int k = 0; k < NP; ++k) { lo_out[k] = 0.0; hi_out[k] = 0.0; }
+    for (int k = 0; k < sc.n; ++k) {
+        double lo = p0[k], hi = p0[k];
+        for (int a = 0; a < m; ++a) {
+            const double b = basis[(size_t)a * NP + k];
+            const double e0 = -2 * EPS * b, e1 = (len[a] + 2 * EPS) * b;
+            lo += e0 < e1 ? e0 : e1;
+            hi += e0 < e1 ? e1 : e0;
+        }
+        const double mg = 0.03 + 1e-9 * (fabs(lo) + fabs(hi));
+        lo_out[k] = lo - mg;
+        hi_out[k] = hi + mg;
+    }
+}
+/* DIRECTIONAL lights whose shadow direction is (nearly) parallel to the orthotope's flat: |P|^2 < EPS with the
+ * intersection's own arithmetic (orthotope.c:170-196); bit L = light L */
+template <int NP>
+__device__ __forceinline__ uint32_t orthotope_parallel_lights(const Scene &sc, const ndt_flat_object *fo)
+{
+    const int m = fo->n_axes;
+    const double *g = sc.geom + fo->geom_off, *p0 = g, *basis = g + NP, *len = basis + (size_t)m * NP;
+    const double *bdb = len + m, *bdp = bdb + m;
+    uint32_t mask = 0;
+    for (int l = 0; l < sc.n_lights && l < 31; ++l) {
+        if (sc.lights[l].type != NDT_L_DIRECTIONAL) continue;
+        double v[NP], o[NP], P[NP], Q[NP];
+        const double *lv = sc.geom + sc.lights[l].vec_off;
+        for (int k = 0; k < NP; ++k) { v[k] = lv[2 * NP + k]; o[k] = 0.0; }
+        axes_PQ<NP, LdGlobal>(o, v, p0, basis, bdb, bdp, m, P, Q);
+        const double qa = vdot<NP>(P, P);
+        if (!(qa >= EPS)) mask |= 1u << l;
+    }
+    return mask;
+}
+__device__ __forceinline__ bool hcube_of_orthotopes(const Scene &sc, const ndt_flat_object *fo)
+{
+    if (fo->child_count <= 0) return false;
+    for (int ch = fo->child_begin; ch < fo->child_begin + fo->child_count; ++ch)
+        if (sc.obj[ch].type != NDT_T_ORTHOTOPE) return false;
+    return true;
+}
+
+/* leaf_refs[] -> LeafRec stream: one thread per reference, once per uploaded scene.  id_base >= 0: the
+ * records of objects id_base .. id_base + n_refs - 1 instead (the face lists nested in hcubes, warp_nested) */
+template <int NP>
+__global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out, BoxRec<NP> *box_out, int id_base)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_refs) return;
-    const int id = sc.leaf[i];
+    const int id = id_base >= 0 ? id_base + i : sc.leaf[i];
     const double *bs = sc.bs + (size_t)id * (NP + 2);
     const ndt_flat_object *fo = sc.obj + id;
     LeafRec<NP> r;
@@ -116,36 +166,38 @@ __global__ void k_pack_leaf(const Scene sc, int n_refs, LeafRec<NP> *out, BoxRec
     BoxRec<NP> bx;
     for (int k = 0; k < NP; ++k) { bx.lo[k] = -FLT_MAX; bx.hi[k] = FLT_MAX; }
     if (fo->type == NDT_T_ORTHOTOPE && bs[NP] > 0) {
-        /* the box of everything the orthotope can report as a hit (see box_hit in warp.cuh):
-         * p0 + sum s_a b_a, s_a in [-EPS, len_a + EPS], thickened by sqrt(2 EPS) = 0.0142; margins doubled */
-        const int m = fo->n_axes;
-        const double *g = sc.geom + fo->geom_off, *p0 = g, *basis = g + NP, *len = basis + (size_t)m * NP;
-        const double *bdb = len + m, *bdp = bdb + m;
+        double lo[NP], hi[NP];
+        orthotope_reach<NP>(sc, fo, lo, hi);
         for (int k = 0; k < sc.n; ++k) {
-            double lo = p0[k], hi = p0[k];
-            for (int a = 0; a < m; ++a) {
-                const double b = basis[(size_t)a * NP + k];
-                const double e0 = -2 * EPS * b, e1 = (len[a] + 2 * EPS) * b;
-                lo += e0 < e1 ? e0 : e1;
-                hi += e0 < e1 ? e1 : e0;
-            }
-            const double mg = 0.03 + 1e-9 * (fabs(lo) + fabs(hi));
             /* stored as float, rounded outwards */
-            bx.lo[k] = __double2float_rd(lo - mg);
-            bx.hi[k] = __double2float_ru(hi + mg);
+            bx.lo[k] = __double2float_rd(lo[k]);
+            bx.hi[k] = __double2float_ru(hi[k]);
         }
         r.boxed = 1;
-        /* DIRECTIONAL lights whose shadow direction is (nearly) parallel to the flat: |P|^2 < EPS with
-         * the intersection's own arithmetic (orthotope.c:170-196) */
-        for (int l = 0; l < sc.n_lights && l < 31; ++l) {
-            if (sc.lights[l].type != NDT_L_DIRECTIONAL) continue;
-            double v[NP], o[NP], P[NP], Q[NP];
-            const double *lv = sc.geom + sc.lights[l].vec_off;
-            for (int k = 0; k < NP; ++k) { v[k] = lv[2 * NP + k]; o[k] = 0.0; }
-            axes_PQ<NP, LdGlobal>(o, v, p0, basis, bdb, bdp, m, P, Q);
-            const double qa = vdot<NP>(P, P);
-            if (!(qa >= EPS)) r.par_mask |= 1u << l;
+        r.par_mask |= orthotope_parallel_lights<NP>(sc, fo);
+    }
+    else if (fo->type == NDT_T_HCUBE && bs[NP] > 0 && sc.any_boxed && hcube_of_orthotopes(sc, fo)) {
+        /* an hcube reports what one of its faces reports (hcube.c:236-250: trace() over the face list, the cube
+         * only replaces the object pointer): the union of the faces' boxes bounds every hit point, and a shadow
+         * direction that must not be culled for one face must not be culled for the cube.  The cube's bounding
+         * sphere is that of its corners, its box far smaller: of the rays that pass the sphere of a randomly
+         * turned 6-cube one in eight meets the box (BASELINE config 3; each of the others cost a pass over
+         * the cube's 472 faces). */
+        double lo[NP], hi[NP];
+        for (int k = 0; k < NP; ++k) { lo[k] = DBL_MAX; hi[k] = -DBL_MAX; }
+        uint32_t pm = 0;
+        for (int ch = fo->child_begin; ch < fo->child_begin + fo->child_count; ++ch) {
+            double cl[NP], chh[NP];
+            orthotope_reach<NP>(sc, sc.obj + ch, cl, chh);
+            for (int k = 0; k < sc.n; ++k) { lo[k] = cl[k] < lo[k] ? cl[k] : lo[k]; hi[k] = chh[k] > hi[k] ? chh[k] : hi[k]; }
+            pm |= orthotope_parallel_lights<NP>(sc, sc.obj + ch);
         }
+        for (int k = 0; k < sc.n; ++k) {
+            bx.lo[k] = __double2float_rd(lo[k]);
+            bx.hi[k] = __double2float_ru(hi[k]);
+        }
+        r.boxed = 1;
+        r.par_mask |= pm;
     }
     else if (bs[NP] > 0 && sc.any_boxed) {
         /* any other primitive with a bounding sphere: the sphere's own box.  A ray that misses it misses the
@@ -182,7 +234,10 @@ __global__ void __launch_bounds__(BLOCK, NDT_MIN_BLOCKS) k_generation(const Scen
     RayIn<NP> *rays = (RayIn<NP> *)a.rays;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage<NP> ws;
-    if (!CNT) ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
+    if (!CNT) {
+        ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
+        ws.init_nested(sc.any_boxed);
+    }
 
     while (true) {
         int base = 0;
@@ -511,7 +566,7 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, con
 }
 
 /* MODE 0: the batch's own rays, MODE 1: its shadow queries */
-template <int NP, int MODE>
+template <int NP, int MODE, bool BIG>
 __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Scene sc, const WaveArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -531,25 +586,25 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
     mb.dirty = ~0ull;            /* first clear() wipes the whole column */
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage<NP> ws;
-    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
+    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed), a.leafrec, sc.any_boxed ? a.boxrec : nullptr, lane);
+    ws.init_nested(sc.any_boxed);
     int kd_overflow = 0;
     int *next = MODE ? &st->next1 : &st->next0;
 
-#ifndef NDT_TRACE_DRAW
-#define NDT_TRACE_DRAW 1     /* 32-ray bundles per draw of the work counter: 4 measured 7-10 % slower (the heavy bundles of a silhouette end up in one warp) */
-#endif
+    /* Rays per draw of the work counter: one bundle of 32.  128 per draw measured 7-10 % slower (the heavy bundles
+     * of a silhouette end up in one warp); spreading a launch that has fewer rays than the resident warps could
+     * take thinner (16 ... 1 rays per draw) measured 6-17 % slower on every workload (one more trip to the counter
+     * per draw, the same leaves staged by more warps): profiles/r02_experiments.md. */
+    constexpr int draw = 32;
     bool stop = false;
     while (!stop) {
         /* (fetching the counter one batch ahead was measured slower: profiles/r01_experiments.md) */
-        int base0 = 0;
-        if (lane == 0) base0 = atomicAdd(next, 32 * NDT_TRACE_DRAW);
-        base0 = __shfl_sync(FULL, base0, 0);
-        if (base0 >= count) break;
-        NDT_NO_UNROLL
-        for (int kk = 0; kk < NDT_TRACE_DRAW; ++kk) {
-            const int base = base0 + 32 * kk;
-            if (base >= count) break;
-            const int r = base + lane;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(next, draw);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        {
+            const int r = lane < draw ? base + lane : count;      /* lanes beyond the draw idle through the query */
             double o[NP], v[NP], limit = -1.0;
             bool want;
             int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
@@ -566,7 +621,7 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
                 }
             }
             Hit T;
-            trace_kd_warp<NP>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
+            trace_kd_warp<NP, BIG>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
             if (ws.fault) { stop = true; break; }     /* warp-uniform (warp.cuh) */
             if (want) {
                 if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), T.t, T.id, T.win, T.found);
@@ -928,7 +983,8 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
     mb.dirty = ~0ull;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage<NP> ws;
-    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed != 0), leafrec, sc.any_boxed ? boxrec : nullptr, lane);
+    ws.init(smem_raw + (threadIdx.x >> 5) * warp_smem_bytes<NP>(sc.any_boxed), leafrec, sc.any_boxed ? boxrec : nullptr, lane);
+    ws.init_nested(sc.any_boxed);
     int ovf = 0;
     /* a warp takes 32 consecutive rays at a time; the loop bound is the same for all of its lanes */
     for (int r0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; r0 < n_rays; r0 += gridDim.x * blockDim.x) {
@@ -941,7 +997,7 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
             v[i] = (want && i < sc.n) ? v_in[(size_t)r * sc.n + i] : 0.0;
         }
         Hit T;
-        trace_kd_warp<NP>(sc, ws, mb, want, o, v, (want && limits) ? limits[r] : -1.0, T, ovf, -1);
+        trace_kd_warp<NP, true>(sc, ws, mb, want, o, v, (want && limits) ? limits[r] : -1.0, T, ovf, -1);
         if (want) {
             double p[NP], nr[NP];
             vzero<NP>(p); vzero<NP>(nr);
@@ -959,21 +1015,21 @@ k_trace_rays(const Scene sc, int n_rays, const double *o_in, const double *v_in,
 
 /* launchers of one NP, filled in by np_inst.cu */
 struct NpOps {
-    int (*trace_blocks_per_sm)(bool boxed);
+    int (*trace_blocks_per_sm)(int boxed);
     void (*trace)(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
     void (*shade)(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
 
-    int (*blocks_per_sm)(bool cnt, bool boxed);
+    int (*blocks_per_sm)(bool cnt, int boxed);
     void (*generation)(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a);
-    void (*pack_leaf)(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out);
+    void (*pack_leaf)(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out, int id_base);
     void (*trace_rays)(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const double *o, const double *v,
                        const double *limits, int32_t *found, int32_t *ids, double *ts, double *hits, double *normals,
                        uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
                        const void *leafrec, const void *boxrec);
     /* for the graph nodes of the device-side generation loop (kernels.cu) */
-    const void *(*trace_fn)(int mode);
+    const void *(*trace_fn)(int mode, int stage);   /* stage = Scene::any_boxed: bit 2 selects the big-leaf instantiation */
     const void *(*shade_fn)(int phase);
-    size_t (*trace_smem_bytes)(bool boxed);
+    size_t (*trace_smem_bytes)(int boxed);
     int (*shade_grid)(int sm_count, int gen_cap);   /* blocks of a k_shade launch */
     const void *(*light_fn)();
     void (*light)(int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);

@@ -354,6 +354,8 @@ struct ndt_b200_ctx {
     char *d_blob; size_t blob_cap;
     char *d_leafrec; size_t leafrec_cap;   /* LeafRec<npad>[n_leaf_refs] */
     char *d_boxrec; size_t boxrec_cap;     /* BoxRec<npad>[n_leaf_refs] */
+    char *d_nrec; size_t nrec_cap;         /* LeafRec<npad>[n_objects - n_items]: the objects nested in hcubes (warp_nested) */
+    char *d_nbox; size_t nbox_cap;         /* BoxRec<npad>[n_objects - n_items] */
     ndt_flat_header hdr;
     Scene sc;
     int have_scene;
@@ -369,7 +371,7 @@ struct ndt_b200_ctx {
     int *d_aa_cnt; unsigned long long *d_aa_res;
     double *d_hgeo; size_t hgeo_bytes;   /* hit point + normal per ray of a batch */
     uint32_t *d_qmask; size_t qmask_bytes;
-    int trace_grid[2][8];                /* cached k_trace occupancy per (boxed scene, NP/2) */
+    int trace_grid[8][8];                /* cached k_trace occupancy per (stage mode = Scene::any_boxed: 0, 1, 3; NP/2) */
     char *d_ana; size_t ana_bytes;       /* ANAGLYPH_3D: the two eyes' fp64 frames */
     int *d_ctr;                          /* fused path: [0] tail [1] next [2..3] overflow */
     WaveState *d_state;                  /* device-side generation loop (gen.cuh) */
@@ -387,16 +389,16 @@ struct ndt_b200_ctx {
     int gen_cap_max;                     /* rays per batch of the generation loop */
     uint32_t options;
     ndt_b200_stats last;
-    int grid_blocks[4][8];               /* cached occupancy per (CNT + 2 * boxed scene, NP/2) */
+    int grid_blocks[16][8];               /* cached occupancy per (CNT + 2 * stage mode, NP/2) */
     int light_type[256];                 /* host copy of lights[].type (which lights can ask a shadow query) */
 };
 
 static int grid_for(ndt_b200_ctx *c, int np, bool cnt)
 {
-    int &g = c->grid_blocks[(cnt ? 1 : 0) + (c->sc.any_boxed ? 2 : 0)][np / 2];
+    int &g = c->grid_blocks[(cnt ? 1 : 0) + 2 * (c->sc.any_boxed & 7)][np / 2];
     if (g == 0) {
         const NpOps *ops = ndt_np_ops(np);
-        g = (ops ? ops->blocks_per_sm(cnt, c->sc.any_boxed != 0) : 1) * c->sm_count;
+        g = (ops ? ops->blocks_per_sm(cnt, c->sc.any_boxed) : 1) * c->sm_count;
     }
     return g;
 }
@@ -413,8 +415,8 @@ static int grow(ndt_b200_ctx *c, void **p, size_t *cap, size_t want_bytes)
 
 static int trace_grid_for(ndt_b200_ctx *c, int np)
 {
-    int &g = c->trace_grid[c->sc.any_boxed ? 1 : 0][np / 2];
-    if (g == 0) g = ndt_np_ops(np)->trace_blocks_per_sm(c->sc.any_boxed != 0) * c->sm_count;
+    int &g = c->trace_grid[c->sc.any_boxed & 7][np / 2];
+    if (g == 0) g = ndt_np_ops(np)->trace_blocks_per_sm(c->sc.any_boxed) * c->sm_count;
     return g;
 }
 
@@ -462,7 +464,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
+    cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_nrec); cudaFree(c->d_nbox); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
     cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_hgeo); cudaFree(c->d_qmask);
     cudaFree(c->aa_img.p); cudaFree(c->aa_fin.p); cudaFree(c->aa_u8.p); cudaFree(c->aa_samp.p);
     cudaFree(c->aa_xy[0].p); cudaFree(c->aa_xy[1].p); cudaFree(c->d_aa_cnt); cudaFree(c->d_aa_res);
@@ -579,9 +581,32 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
             CK(cudaMalloc(&c->d_leafrec, need + need / 4));
             c->leafrec_cap = need + need / 4;
         }
+        /* the face lists nested in hcubes get the same two streams and a second staging area per warp
+         * (warp.cuh: warp_nested) when the scene is boxed and every nested object is an orthotope (hcube.c:33-152
+         * creates nothing else); otherwise they stay with the scalar loop */
+        s.nrec = s.nbox = NULL;
+        const int n_nested = h->n_objects - h->n_items;
+        if (s.any_boxed && n_nested > 0 && !getenv("NDT_B200_NO_NESTED_STAGE")) {
+            const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
+            bool all_orthotopes = true;
+            for (int i = h->n_items; i < h->n_objects && all_orthotopes; ++i) all_orthotopes = ho[i].type == NDT_T_ORTHOTOPE;
+            if (all_orthotopes) {
+                if ((r = grow(c, (void **)&c->d_nrec, &c->nrec_cap, (size_t)n_nested * recb))) return r;
+                if ((r = grow(c, (void **)&c->d_nbox, &c->nbox_cap, (size_t)n_nested * (size_t)h->npad * 8))) return r;
+                s.nrec = c->d_nrec; s.nbox = c->d_nbox;
+                s.any_boxed |= 2;
+            }
+        }
+        /* scenes with nested lists or very large leaves run the k_trace instantiation that carries the nested
+         * call and the sparse-warp broad phase (warp.cuh); the others keep the smaller kernel */
+        if (s.any_boxed && ((s.any_boxed & 2) || h->max_leaf >= 2048)) s.any_boxed |= 4;
         if (h->n_leaf_refs > 0) {
             if ((r = grow(c, (void **)&c->d_boxrec, &c->boxrec_cap, (size_t)h->n_leaf_refs * (size_t)h->npad * 8))) return r;
-            ndt_np_ops(h->npad)->pack_leaf(c->stream, s, h->n_leaf_refs, c->d_leafrec, c->d_boxrec);
+            ndt_np_ops(h->npad)->pack_leaf(c->stream, s, h->n_leaf_refs, c->d_leafrec, c->d_boxrec, -1);
+            CK(cudaGetLastError());
+        }
+        if (s.any_boxed & 2) {
+            ndt_np_ops(h->npad)->pack_leaf(c->stream, s, n_nested, c->d_nrec, c->d_nbox, h->n_items);
             CK(cudaGetLastError());
         }
     }
@@ -734,12 +759,12 @@ static int wave_graph_build(ndt_b200_ctx *c, int np, const WaveArgs &a, int n_sh
     cudaGraph_t b1 = p1.conditional.phGraph_out[0];
     Scene sc = c->sc;
     WaveArgs wa = a;
-    const size_t smem = ops->trace_smem_bytes(sc.any_boxed != 0);
+    const size_t smem = ops->trace_smem_bytes(sc.any_boxed);
     void *targs[] = { &sc, &wa };
-    GK(add_kernel(b1, &n_prev, NULL, ops->trace_fn(0), trace_grid, BLOCK, smem, targs));
+    GK(add_kernel(b1, &n_prev, NULL, ops->trace_fn(0, sc.any_boxed), trace_grid, BLOCK, smem, targs));
     GK(add_kernel(b1, &n_cur, &n_prev, ops->shade_fn(0), shade_grid, BLOCK, 0, targs)); n_prev = n_cur;
     if (n_sh > 0) {
-        GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(1), trace_grid, BLOCK, smem, targs)); n_prev = n_cur;
+        GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(1, sc.any_boxed), trace_grid, BLOCK, smem, targs)); n_prev = n_cur;
         GK(add_kernel(b1, &n_cur, &n_prev, ops->light_fn(), light_grid(c), BLOCK, 0, targs)); n_prev = n_cur;
         int spec = c->hdr.specular, aux_word = np;
         void *largs[] = { &wa, &spec, &aux_word };
@@ -891,6 +916,7 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
             WaveState *hs = (WaveState *)(c->h_snap + (size_t)c->n_snap * WAVE_HEAD_BYTES);
             cudaGraphConditionalHandle nohandle = 0;
             int guard = 0;
+            const bool trace_gens = getenv("NDT_B200_TRACE_GENS") != NULL;     /* the size of every generation, on stderr */
             do {
                 ops->trace(0, full_grid, st, c->sc, a);
                 ops->shade(0, shade_grid, st, c->sc, a);
@@ -904,6 +930,8 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(hs, c->d_state, WAVE_HEAD_BYTES, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                if (trace_gens) fprintf(stderr, "ndt_b200: batch %d done -> next: generation %d, slots [%d, %d), cont %d\n",
+                                        hs->iters, hs->gen, hs->start, hs->start + hs->count, hs->cont);
             } while (hs->cont && ++guard < (1 << 20));
             k_pre_resolve<<<1, 32, 0, st>>>(c->d_state, nohandle, 0);
             const int ngen = hs->fail ? 0 : hs->ngen;

@@ -12,9 +12,9 @@
 namespace {
 constexpr int NP = NDT_NP;
 
-template <bool CNT> size_t generation_smem(bool boxed) { return CNT ? 0 : (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(boxed); }
+template <bool CNT> size_t generation_smem(int boxed) { return CNT ? 0 : (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(boxed); }
 
-template <bool CNT> int occ(bool boxed)
+template <bool CNT> int occ(int boxed)
 {
     int b = 0;
     const size_t sm = generation_smem<CNT>(boxed);
@@ -22,31 +22,38 @@ template <bool CNT> int occ(bool boxed)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_generation<NP, CNT>, BLOCK, sm) != cudaSuccess || b < 1) b = 1;
     return b;
 }
-int blocks_per_sm(bool cnt, bool boxed) { return cnt ? occ<true>(boxed) : occ<false>(boxed); }
+int blocks_per_sm(bool cnt, int boxed) { return cnt ? occ<true>(boxed) : occ<false>(boxed); }
 
 void generation(bool cnt, int blocks, cudaStream_t st, const Scene &sc, const GenArgs &a)
 {
-    if (cnt) k_generation<NP, true><<<blocks, BLOCK, generation_smem<true>(sc.any_boxed != 0), st>>>(sc, a);
-    else k_generation<NP, false><<<blocks, BLOCK, generation_smem<false>(sc.any_boxed != 0), st>>>(sc, a);
+    if (cnt) k_generation<NP, true><<<blocks, BLOCK, generation_smem<true>(sc.any_boxed), st>>>(sc, a);
+    else k_generation<NP, false><<<blocks, BLOCK, generation_smem<false>(sc.any_boxed), st>>>(sc, a);
 }
 
-size_t trace_smem(bool boxed) { return (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(boxed); }
-int trace_blocks_per_sm(bool boxed)
+size_t trace_smem(int boxed) { return (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(boxed); }
+template <bool BIG> int trace_occ(int boxed)
 {
     int b0 = 0, b1 = 0;
     const size_t sm = trace_smem(boxed);
     if (sm > 48 * 1024) {
-        cudaFuncSetAttribute(k_trace<NP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cudaFuncSetAttribute(k_trace<NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(k_trace<NP, 0, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaFuncSetAttribute(k_trace<NP, 1, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_trace<NP, 0>, BLOCK, sm) != cudaSuccess || b0 < 1) b0 = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<NP, 1>, BLOCK, sm) != cudaSuccess || b1 < 1) b1 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_trace<NP, 0, BIG>, BLOCK, sm) != cudaSuccess || b0 < 1) b0 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_trace<NP, 1, BIG>, BLOCK, sm) != cudaSuccess || b1 < 1) b1 = 1;
     return b0 < b1 ? b0 : b1;
 }
+int trace_blocks_per_sm(int boxed) { return (boxed & 4) ? trace_occ<true>(boxed) : trace_occ<false>(boxed); }
 void trace(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
 {
-    if (mode) k_trace<NP, 1><<<blocks, BLOCK, trace_smem(sc.any_boxed != 0), st>>>(sc, a);
-    else k_trace<NP, 0><<<blocks, BLOCK, trace_smem(sc.any_boxed != 0), st>>>(sc, a);
+    const size_t sm = trace_smem(sc.any_boxed);
+    if (sc.any_boxed & 4) {
+        if (mode) k_trace<NP, 1, true><<<blocks, BLOCK, sm, st>>>(sc, a);
+        else k_trace<NP, 0, true><<<blocks, BLOCK, sm, st>>>(sc, a);
+    } else {
+        if (mode) k_trace<NP, 1, false><<<blocks, BLOCK, sm, st>>>(sc, a);
+        else k_trace<NP, 0, false><<<blocks, BLOCK, sm, st>>>(sc, a);
+    }
 }
 void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
 {
@@ -54,7 +61,11 @@ void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveAr
     else k_shade<NP, 0><<<blocks, BLOCK, 0, st>>>(sc, a);
 }
 
-const void *trace_fn(int mode) { return mode ? (const void *)k_trace<NP, 1> : (const void *)k_trace<NP, 0>; }
+const void *trace_fn(int mode, int stage)
+{
+    if (stage & 4) return mode ? (const void *)k_trace<NP, 1, true> : (const void *)k_trace<NP, 0, true>;
+    return mode ? (const void *)k_trace<NP, 1, false> : (const void *)k_trace<NP, 0, false>;
+}
 const void *shade_fn(int phase) { return phase ? (const void *)k_shade<NP, 1> : (const void *)k_shade<NP, 0>; }
 int shade_grid(int sm_count, int gen_cap)
 {
@@ -73,9 +84,9 @@ int shade_grid(int sm_count, int gen_cap)
 const void *light_fn() { return (const void *)k_light<NP>; }
 void light(int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a) { k_light<NP><<<blocks, BLOCK, 0, st>>>(sc, a); }
 
-void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out)
+void pack_leaf(cudaStream_t st, const Scene &sc, int n_refs, void *out, void *box_out, int id_base)
 {
-    k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out, (BoxRec<NP> *)box_out);
+    k_pack_leaf<NP><<<(n_refs + 255) / 256, 256, 0, st>>>(sc, n_refs, (LeafRec<NP> *)out, (BoxRec<NP> *)box_out, id_base);
 }
 
 void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const double *o, const double *v,
@@ -83,7 +94,7 @@ void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const 
                 uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
                 const void *leafrec, const void *boxrec)
 {
-    const size_t sm = (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(sc.any_boxed != 0);
+    const size_t sm = (size_t)(BLOCK / 32) * warp_smem_bytes<NP>(sc.any_boxed);
     if (sm > 48 * 1024) cudaFuncSetAttribute(k_trace_rays<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     k_trace_rays<NP><<<blocks, BLOCK, sm, st>>>(
         sc, n_rays, o, v, limits, found, ids, ts, hits, normals, mb_bits, mb_stride, mb_words, mb_shift, overflow, leafrec, boxrec);

@@ -92,11 +92,17 @@ __host__ __device__ inline int geom_block_doubles(int type, int m, int np)
 }
 
 /* per warp: two LeafRec chunks, two geometry blocks, four mbarriers and -- only for scenes with boxed
- * primitives -- two BoxRec chunks (dynamic shared memory: the launch asks for what the scene needs) */
-template <int NP> __host__ __device__ constexpr int warp_smem_bytes(bool boxed)
+ * primitives -- two BoxRec chunks (dynamic shared memory: the launch asks for what the scene needs).
+ * `mode` is Scene::any_boxed: bit 0 = boxes are staged, bit 1 = a second, identical staging area for the
+ * face lists nested in hcubes (warp_nested). */
+template <int NP> __host__ __device__ constexpr int warp_stage_bytes(bool boxed)
 {
     return 2 * CHUNK * (int)sizeof(LeafRec<NP>) + 2 * geom_max_doubles<NP>() * 8 + 32 +
            (boxed ? 2 * CHUNK * (int)sizeof(BoxRec<NP>) + NP * 16 : 0);     /* + the ray bundle's bounds */
+}
+template <int NP> __host__ __device__ constexpr int warp_smem_bytes(int mode)
+{
+    return warp_stage_bytes<NP>((mode & 1) != 0) * ((mode & 2) ? 2 : 1);
 }
 
 /* ---- mbarrier + TMA bulk copy (PTX ISA: cp.async.bulk, mbarrier) ------------- */
@@ -147,9 +153,42 @@ template <int NP> struct WarpStage {
     const BoxRec<NP> *boxes;   /* NULL: the scene has no boxed primitive */
     int lane;
     int fault;            /* a bounded wait ran out */
+    unsigned char *nest;  /* the second staging area (hcube face lists), NULL: none */
+    uint32_t nphase;      /* its barrier parities */
+
+    /* lay the pointers over a staging area (no barrier initialisation) */
+    __device__ __forceinline__ void place(unsigned char *smem)
+    {
+        buf0 = reinterpret_cast<LeafRec<NP> *>(smem);
+        gbuf0 = reinterpret_cast<double *>(buf0 + 2 * CHUNK);
+        bar = reinterpret_cast<uint64_t *>(gbuf0 + 2 * geom_max_doubles<NP>());
+        bbuf0 = reinterpret_cast<BoxRec<NP> *>(bar + 4);        /* present only when boxes != NULL */
+        bundle = reinterpret_cast<float4 *>(bbuf0 + 2 * CHUNK); /* likewise */
+    }
+    /* mode & 2 (Scene::any_boxed): the launch reserved a second area behind the first */
+    __device__ __forceinline__ void init_nested(int mode)
+    {
+        nest = nullptr;
+        nphase = 0;
+        if (mode & 2) {
+            nest = reinterpret_cast<unsigned char *>(buf0) + warp_stage_bytes<NP>(true);
+            if (lane == 0) {
+                uint64_t *nb = reinterpret_cast<uint64_t *>(nest + 2 * CHUNK * sizeof(LeafRec<NP>) + 2 * geom_max_doubles<NP>() * 8);
+                mbar_init(nb, 1);
+                mbar_init(nb + 1, 1);
+                mbar_init(nb + 2, 1);
+                mbar_init(nb + 3, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncwarp();
+        }
+    }
 
     __device__ __forceinline__ void init(unsigned char *smem, const void *leafrec, const void *boxrec, int lane_)
     {
+        nest = nullptr;
+        nphase = 0;
         buf0 = reinterpret_cast<LeafRec<NP> *>(smem);
         boxes = static_cast<const BoxRec<NP> *>(boxrec);
         gbuf0 = reinterpret_cast<double *>(buf0 + 2 * CHUNK);
@@ -246,6 +285,20 @@ template <int NP> __device__ __forceinline__ bool box_hit(const float *lo, const
         }
     }
     /* one more ulp-scale allowance on the comparison itself */
+    return tmin <= tmax * 1.000001f + 1e-30f;
+}
+
+/* box_hit on a box held in registers (the sparse-warp form of the broad phase): the same operations in the same order */
+template <int NP> __device__ __forceinline__ bool box_hit_regs(const float *lo, const float *hi, const float *of, const float *vif)
+{
+    float tmin = 0.0f, tmax = FLT_MAX;
+    NDT_UNROLL
+    for (int i = 0; i < NP; ++i) {
+        const float t1 = __fmul_rn(__fsub_rn(lo[i], of[i]), vif[i]);
+        const float t2 = __fmul_rn(__fsub_rn(hi[i], of[i]), vif[i]);
+        tmin = fmaxf(tmin, fminf(t1, t2));
+        tmax = fminf(tmax, fmaxf(t1, t2));
+    }
     return tmin <= tmax * 1.000001f + 1e-30f;
 }
 
@@ -352,10 +405,239 @@ __device__ __forceinline__ double trace_list_slow(const Scene &sc, const int32_t
     return trace_list_slow_impl<NP>(sc, ids, cnt, base, ot, vt, dist_limit, out_id, out_win);
 }
 
+template <int NP, bool NESTED, bool BIG>
+__device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, int first, int count, bool mine,
+                                            Mailbox &mb, const double *o, const double *v, const float *obox,
+                                            const float *vbox, uint32_t keep_mask, double dist_limit,
+                                            int &out_id, int &out_win);
+
+/* The face list nested in an hcube (hcube.c:236-250: trace() over hcube->obj with no mailbox, no limit, its own
+ * min_dist) for the lanes with `mine`, through the SECOND staging area of the warp: the same record / box streams,
+ * bundle cull, fp32 slab test, sphere pre-test and staged narrow phase as a kd leaf gets.  The scalar loop
+ * (core.cuh: trace_list) tested the bounding sphere of every face for every ray that passed the cube's own
+ * sphere -- 472 faces for a 6-cube, 98 % of the FP64 work of BASELINE config 3.  Out of line: one copy, and
+ * the caller's registers (its ray, its leaf state) are not the nested loop's problem. */
+template <int NP>
+__device__ __noinline__ double warp_nested(const Scene &sc, unsigned char *area, float4 *bundle, int lane, int first,
+                                           int count, bool mine, const double *o_in, const double *v_in,
+                                           const float *obox, const float *vbox, uint32_t keep_mask,
+                                           uint32_t *phase_io, int *fault_io, int *out_win)
+{
+    WarpStage<NP> wn;
+    wn.place(area);
+    wn.bundle = bundle;                 /* the rays of this call are a subset of the bundle's: the cull stays valid */
+    wn.stream = static_cast<const LeafRec<NP> *>(sc.nrec);
+    wn.boxes = static_cast<const BoxRec<NP> *>(sc.nbox);
+    wn.lane = lane;
+    wn.phase = *phase_io;
+    wn.fault = *fault_io;
+    wn.nest = nullptr;
+    wn.nphase = 0;
+    double o[NP], v[NP];
+    vcopy<NP>(o, o_in);
+    vcopy<NP>(v, v_in);
+    Mailbox none;
+    none.bits = nullptr; none.stride = 0; none.slot = 0; none.words = 0; none.group_shift = 0; none.dirty = 0;
+    int oid, owin;
+    const double md = warp_leaf<NP, true, true>(sc, wn, first, count, mine, none, o, v, obox, vbox, keep_mask, -1.0, oid, owin);
+    *phase_io = wn.phase;
+    *fault_io = wn.fault;
+    *out_win = owin;
+    return md;
+}
+
+/* The face list of an hcube for ONE ray (lane L's), the 32 lanes side by side on 32 faces: what warp_nested does
+ * for a bundle, for the incoherent warps of the bounce generations, where one or two lanes ask for a cube and
+ * walking its list in step leaves 30 lanes idle.
+ *   1. every lane runs the slab test and the ray half of the sphere pre-test for its face (boxes and records
+ *      straight from global memory, 15 rounds for the 472 faces of a 6-cube); the faces that pass are
+ *      appended, in list order, to a list in shared memory;
+ *   2. whenever 32 are listed (and at the end) each lane intersects ONE of them -- a pure function of
+ *      (face, ray): the nested trace() has no mailbox and no limit, and every face is an orthotope, whose
+ *      intersect() overwrites hit and normal before it reads them;
+ *   3. the results are folded in list order with trace()'s own rule (object.c:715-727) and, in front of it, the
+ *      min_dist half of the pre-test (bounding.c:43-50), which only decides whether a face is asked at all.
+ * Returns the nested trace()'s min_dist (< 0: nothing accepted) and the winning face, identical in every lane. */
+template <int NP>
+__device__ __noinline__ double hcube_one_ray(const Scene &sc, int32_t *list, int lane, int L, int first, int count,
+                                             const double *o_in, const double *v_in, const float *obox,
+                                             const float *vbox, uint32_t keep_mask, int *out_win)
+{
+    const LeafRec<NP> *recs = static_cast<const LeafRec<NP> *>(sc.nrec) + first;
+    const BoxRec<NP> *boxes = static_cast<const BoxRec<NP> *>(sc.nbox) + first;
+    double o[NP], v[NP];
+    float of[NP], vif[NP];
+    NDT_UNROLL
+    for (int i = 0; i < NP; ++i) {
+        o[i] = __shfl_sync(FULL, o_in[i], L);
+        v[i] = __shfl_sync(FULL, v_in[i], L);
+        of[i] = __shfl_sync(FULL, obox[i], L);
+        vif[i] = __shfl_sync(FULL, vbox[i], L);
+    }
+    const uint32_t km = __shfl_sync(FULL, keep_mask, L);
+    double in_min = -1;
+    int win = -1, n_list = 0;
+    const int rounds = (count + 31) >> 5;
+    for (int rd = 0; rd <= rounds; ++rd) {
+        if (rd < rounds) {
+            const int f = rd * 32 + lane;
+            bool pass = false;
+            if (f < count) {
+                const double *rp = reinterpret_cast<const double *>(recs + f);
+                const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);        /* boxed, par_mask */
+                pass = true;
+                if (bx.x && !(bx.y & km)) {
+                    float lo[NP], hi[NP];
+                    NDT_UNROLL
+                    for (int i = 0; i < NP; i += 2) {
+                        const float2 l2 = *reinterpret_cast<const float2 *>(boxes[f].lo + i);
+                        const float2 h2 = *reinterpret_cast<const float2 *>(boxes[f].hi + i);
+                        lo[i] = l2.x; lo[i + 1] = l2.y; hi[i] = h2.x; hi[i + 1] = h2.y;
+                    }
+                    pass = box_hit_regs<NP>(lo, hi, of, vif);
+                }
+                if (pass) {
+                    double c[NP];
+                    NDT_UNROLL
+                    for (int i = 0; i < NP; ++i) c[i] = rp[i];
+                    const double r2 = rp[NP], r = rp[NP + 1];
+                    pass = !(r > 0) || bsphere_ray_part<NP>(c, r2, o, v);
+                }
+            }
+            const unsigned m = __ballot_sync(FULL, pass);
+            if (pass) list[n_list + __popc(m & ((1u << lane) - 1u))] = f;
+            n_list += __popc(m);
+            __syncwarp();
+        }
+        /* a full batch, or what is left after the last round */
+        while (n_list >= 32 || (rd == rounds && n_list > 0)) {
+            const int nb = n_list < 32 ? n_list : 32;
+            bool ret = false;
+            double dist = -1, oc2 = 0, rad = 0;
+            int f = -1;
+            if (lane < nb) {
+                f = list[lane];
+                const double *rp = reinterpret_cast<const double *>(recs + f);
+                const int4 meta = *reinterpret_cast<const int4 *>(rp + NP + 2);
+                double c[NP], oc[NP];
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) c[i] = rp[i];
+                rad = rp[NP + 1];
+                vsub<NP>(o, c, oc);
+                oc2 = vdot<NP>(oc, oc);                 /* bsphere_far's own arithmetic */
+                ndt_flat_object fo;
+                fo.type = NDT_T_ORTHOTOPE;
+                fo.flags = (int32_t)(((uint32_t)meta.y >> 4) & 0xfu);
+                fo.n_axes = (int32_t)(((uint32_t)meta.y >> 8) & 0xffu);
+                fo.geom_off = (uint32_t)meta.z;
+                fo.report_id = meta.w;
+                Tally<false> none;
+                double res[NP], nrm[NP];
+                vzero<NP>(res);
+                vzero<NP>(nrm);
+                ret = intersect_prim<NP, false, LdGlobal>(sc, fo, sc.geom + fo.geom_off, o, v, res, nrm, none);
+                if (ret) dist = vdist<NP>(o, res);
+            }
+            __syncwarp();
+            /* the faces that were not listed failed the pre-test; the listed ones that report no hit change nothing */
+            for (unsigned hm = __ballot_sync(FULL, ret); hm; hm &= hm - 1) {
+                const int src = __ffs(hm) - 1;
+                const double d = __shfl_sync(FULL, dist, src), q = __shfl_sync(FULL, oc2, src), r = __shfl_sync(FULL, rad, src);
+                const int fid = __shfl_sync(FULL, f, src);
+                if (r > 0 && in_min > 0) {              /* bounding.c:43-50 with the min_dist of this point of the list */
+                    const double mr = in_min + r;
+                    if (q > mr * mr) continue;
+                }
+                if (d > EPS && (d + EPS < in_min || in_min < 0)) {
+                    in_min = d;
+                    win = fid;
+                }
+            }
+            /* move the rest of the list to the front */
+            int keep = -1;
+            if (lane + nb < n_list) keep = list[lane + nb];
+            __syncwarp();
+            if (lane + nb < n_list) list[lane] = keep;
+            n_list -= nb;
+            __syncwarp();
+        }
+    }
+    *out_win = win >= 0 ? first + win + sc.n_items : -1;
+    return in_min;
+}
+
+/* One hcube of a kd leaf whose face list goes through the second staging area (warp_nested): the whole warp
+ * stages it for the lanes that ask (`want`: live, and a candidate of the broad phase). */
+template <int NP>
+__device__ __forceinline__ void warp_hcube(const Scene &sc, WarpStage<NP> &ws, const double *rp, const int4 meta, bool want,
+                                           Mailbox &mb, const double *o, const double *v, const float *obox, const float *vbox,
+                                           uint32_t keep_mask, double dist_limit, double &min_dist, int &out_id, int &out_win,
+                                           bool &live)
+{
+    const int id = meta.x;
+    bool test = want;
+    if (test) {                                /* object.c:706-713, bounding.c:43-50 */
+        uint32_t *mword = mb.word((uint32_t)id >> 5);
+        const uint32_t mcur = *mword, mbit = 1u << (id & 31);
+        if (mcur & mbit) test = false;
+        else {
+            *mword = mcur | mbit;
+            mb.dirty |= 1ull << (((uint32_t)id >> 5) >> mb.group_shift);
+        }
+        const double2 rr = *reinterpret_cast<const double2 *>(rp + NP);
+        if (test && rr.y > 0) {
+            double c[NP];
+            lds_vec<NP>(c, rp);
+            if (bsphere_far<NP>(c, rr.y, o, min_dist)) test = false;
+        }
+    }
+    const unsigned asking = __ballot_sync(FULL, test);
+    if (asking) {
+        /* nested trace() (hcube.c:236-250): no mailbox, no limit, own min_dist */
+        const ndt_flat_object *top = sc.obj + id;
+        const int cb = NDT_LDG(&top->child_begin), cc = NDT_LDG(&top->child_count);
+        double ot[NP], vt[NP];
+        vcopy<NP>(ot, o);
+        vcopy<NP>(vt, v);
+        double in_min = -1;
+        int cwin = -1;
+#ifndef NDT_HCUBE_ONE_RAY_MAX
+#define NDT_HCUBE_ONE_RAY_MAX 6       /* up to this many lanes asking: one ray at a time across the lanes */
+#endif
+        if (__popc(asking) <= NDT_HCUBE_ONE_RAY_MAX) {
+            /* the second staging area is idle here: its first 256 bytes hold the candidate list (63 entries at most) */
+            for (unsigned am = asking; am; am &= am - 1) {
+                const int L = __ffs(am) - 1;
+                int w1 = -1;
+                const double m1 = hcube_one_ray<NP>(sc, reinterpret_cast<int32_t *>(ws.nest), ws.lane, L, cb - sc.n_items, cc, ot, vt,
+                                                    obox, vbox, keep_mask, &w1);
+                if (ws.lane == L) { in_min = m1; cwin = w1; }
+            }
+        } else {
+            uint32_t ph = ws.nphase;
+            int fl = ws.fault;
+            in_min = warp_nested<NP>(sc, ws.nest, ws.bundle, ws.lane, cb - sc.n_items, cc, test, ot, vt,
+                                     obox, vbox, keep_mask, &ph, &fl, &cwin);
+            ws.nphase = ph;
+            ws.fault = fl;
+        }
+        if (test && !(in_min < 0)) {
+            const double dist = in_min;
+            if (dist > EPS && (dist + EPS < min_dist || min_dist < 0)) {
+                min_dist = dist;
+                out_id = meta.w;
+                out_win = cwin;
+            }
+            if (dist_limit == 0.0 || dist < dist_limit) live = false;
+        }
+    }
+}
+
 /* trace() (object.c:692-747) of one leaf for the lanes with `mine`, all 32
  * lanes of the warp taking part in the staging.  Per lane on return: min_dist
- * (<0: nothing accepted), out_id, out_win. */
-template <int NP>
+ * (<0: nothing accepted), out_id, out_win.  NESTED: the face list of an hcube (warp_nested): every record is
+ * an orthotope, no mailbox, dist_limit -1. */
+template <int NP, bool NESTED, bool BIG>
 __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, int first, int count, bool mine,
                                             Mailbox &mb, const double *o, const double *v, const float *obox,
                                             const float *vbox, uint32_t keep_mask, double dist_limit,
@@ -401,6 +683,50 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
             surv = __ballot_sync(FULL, keep);
         }
 #endif
+        /* A SPARSE warp (few live rays: the late bounce generations, warps drawn short by k_trace) turns the
+         * slab test round as well: one ray at a time, lane k testing record k for it -- R rounds instead of one
+         * round per surviving record.  Same function of the same (ray, record) pair, so the same candidates. */
+        unsigned own = surv;            /* the records this lane's ray still has to look at */
+        const int n_live = BIG ? __popc(__ballot_sync(FULL, live)) : 32;
+#ifndef NDT_NO_SPARSE_BROAD
+        const bool sparse = BIG && ws.boxes && n_live * 3 < __popc(surv) * 2;
+#else
+        const bool sparse = false;
+#endif
+        if (sparse) {
+            float lo[NP], hi[NP];
+            uint2 bx = make_uint2(0u, 0u);
+            const bool have = ws.lane < cnt && ((surv >> ws.lane) & 1u);
+            if (have) {
+                bx = *reinterpret_cast<const uint2 *>(reinterpret_cast<const double *>(rec + ws.lane) + NP + 4);
+                NDT_UNROLL
+                for (int i = 0; i < NP; i += 4) {
+                    const float4 l4 = *reinterpret_cast<const float4 *>(brec[ws.lane].lo + i);
+                    const float4 h4 = *reinterpret_cast<const float4 *>(brec[ws.lane].hi + i);
+                    lo[i] = l4.x; hi[i] = h4.x;
+                    if (i + 1 < NP) { lo[i + 1] = l4.y; hi[i + 1] = h4.y; }
+                    if (i + 2 < NP) { lo[i + 2] = l4.z; hi[i + 2] = h4.z; }
+                    if (i + 3 < NP) { lo[i + 3] = l4.w; hi[i + 3] = h4.w; }
+                }
+            } else {
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) { lo[i] = 0.0f; hi[i] = 0.0f; }
+            }
+            float of[NP], vif[NP];
+            NDT_UNROLL
+            for (int i = 0; i < NP; ++i) { of[i] = live ? obox[i] : 0.0f; vif[i] = live ? vbox[i] : 0.0f; }
+            NDT_NO_UNROLL
+            for (unsigned am = __ballot_sync(FULL, live); am; am &= am - 1) {
+                const int L = __ffs(am) - 1;
+                float ol[NP], vl[NP];
+                NDT_UNROLL
+                for (int i = 0; i < NP; ++i) { ol[i] = __shfl_sync(FULL, of[i], L); vl[i] = __shfl_sync(FULL, vif[i], L); }
+                const uint32_t kml = __shfl_sync(FULL, keep_mask, L);
+                const bool pass = have && (!(bx.x && !(bx.y & kml)) || box_hit_regs<NP>(lo, hi, ol, vl));
+                const unsigned m = __ballot_sync(FULL, pass);
+                if (ws.lane == L) own = m;
+            }
+        }
         if (live) {
             if (ws.boxes) {
                 /* boxed scene: the fp32 slab test first, the sphere test for what is left */
@@ -408,12 +734,13 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                 NDT_UNROLL
                 for (int i = 0; i < NP; ++i) { of[i] = obox[i]; vif[i] = vbox[i]; }
                 NDT_BROAD_LOOP
-                for (unsigned sm = surv; sm; sm &= sm - 1) {
+                for (unsigned sm = own; sm; sm &= sm - 1) {
                     const int k = __ffs(sm) - 1;
                     const double *rp = reinterpret_cast<const double *>(rec + k);
                     const uint2 bx = *reinterpret_cast<const uint2 *>(rp + NP + 4);    /* boxed, par_mask */
                     bool pass = true;
-                    if (bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(brec[k].lo, brec[k].hi, of, vif);
+                    /* (a sparse warp's `own` already went through the slab test) */
+                    if (!sparse && bx.x && !(bx.y & keep_mask)) pass = box_hit<NP>(brec[k].lo, brec[k].hi, of, vif);
                     if (pass) {
                         double c[NP];
                         lds_vec<NP>(c, rp);
@@ -456,10 +783,14 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
             const int4 meta = *reinterpret_cast<const int4 *>(rp + NP + 2);
             const bool staged = ((uint32_t)meta.y >> 16) != 0;
             if (staged) ws.wait(2 + gs);
-            if (live && ((cand >> k) & 1u)) {
-                const int id = meta.x;
+            const int id = meta.x;
+            if (BIG && !NESTED && ((uint32_t)meta.y & 0xfu) == NDT_T_HCUBE && ws.nest) {
+                /* (warp-uniform branch: the record is the same for all lanes) */
+                warp_hcube<NP>(sc, ws, rp, meta, live && ((cand >> k) & 1u), mb, o, v, obox, vbox, keep_mask, dist_limit,
+                               min_dist, out_id, out_win, live);
+            } else if (live && ((cand >> k) & 1u)) {
                 bool skip = false;
-                {                                      /* object.c:706-713 */
+                if (!NESTED) {                         /* object.c:706-713 */
                     uint32_t *mword = mb.word((uint32_t)id >> 5);
                     const uint32_t mcur = *mword, mbit = 1u << (id & 31);
                     if (mcur & mbit) skip = true;
@@ -478,7 +809,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                 }
                 if (!skip) {
                     ndt_flat_object fo;
-                    fo.type = (int32_t)((uint32_t)meta.y & 0xfu);
+                    fo.type = NESTED ? (int32_t)NDT_T_ORTHOTOPE : (int32_t)((uint32_t)meta.y & 0xfu);
                     fo.flags = (int32_t)(((uint32_t)meta.y >> 4) & 0xfu);
                     fo.n_axes = (int32_t)(((uint32_t)meta.y >> 8) & 0xffu);
                     fo.geom_off = (uint32_t)meta.z;
@@ -490,7 +821,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                     if (staged) {
                         ret = intersect_prim<NP, false, LdShared>(sc, fo, ws.gbuf(gs), o, v, res, nrm, none);
                         if (ret) dist = vdist<NP>(o, res);
-                    } else if (fo.type != NDT_T_HCUBE) {
+                    } else if (NESTED || fo.type != NDT_T_HCUBE) {
                         ret = false;        /* unreachable: ndt_b200_upload refuses blocks that cannot be staged */
                     } else {
                         /* nested trace() (hcube.c:236-250): no mailbox, no limit, own min_dist */
@@ -507,7 +838,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
                             out_id = fo.report_id;
                             out_win = win;
                         }
-                        if (dist_limit == 0.0 || dist < dist_limit) live = false;
+                        if (!NESTED && (dist_limit == 0.0 || dist < dist_limit)) live = false;
                     }
                 }
             }
@@ -525,7 +856,7 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
 
 /* trace_kd (object.c:683) for the 32 rays of a warp.  Lanes with !want take
  * part in the staging only.  Same contract as core.cuh's trace_kd. */
-template <int NP>
+template <int NP, bool BIG>
 __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool want,
                                               const double *o, const double *v, double dist_limit,
                                               Hit &out, int &overflow, int dir_light)
@@ -686,7 +1017,7 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
             const bool mine = leaf_node == L;
             waiting &= ~__ballot_sync(FULL, mine);
             int oid, owin;
-            const double lmd = warp_leaf<NP>(sc, ws, first, count, mine, mb, o, v, obox, vbox, keep_mask, dist_limit, oid, owin);
+            const double lmd = warp_leaf<NP, false, BIG>(sc, ws, first, count, mine, mb, o, v, obox, vbox, keep_mask, dist_limit, oid, owin);
             if (mine && !(lmd < 0)) {
                 lret = 1;
                 if (lmd < lt) {          /* trace sets t only when min_dist > EPS, which holds here */
@@ -733,7 +1064,7 @@ __device__ __forceinline__ void process_ray_warp(const Scene &sc, WarpStage<NP> 
             continue;
         }
         Hit T;
-        trace_kd_warp<NP>(sc, ws, mb, want, S.ro, S.rv, S.limit, T, overflow, S.ltype == NDT_L_DIRECTIONAL ? it : -1);
+        trace_kd_warp<NP, true>(sc, ws, mb, want, S.ro, S.rv, S.limit, T, overflow, S.ltype == NDT_L_DIRECTIONAL ? it : -1);
         if (want) shade_after<NP, false>(sc, S, it, T, src, look, rec, prim_hit, prim_id, prim_dist, none);
         if (it < 0 && !__ballot_sync(FULL, active && S.shaded)) break;
     }

@@ -10,7 +10,7 @@ subprocess.run(["g++", "-m64", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"
                 "-I" + ROOT + "/ndt_b200/csrc", "-shared", "-o", so, ROOT + "/tools/workload_stats.cpp", "-lm"], check=True)
 L = C.CDLL(so)
 key = sys.argv[1]
-f = ndt_b200.FlatScene.load(os.path.join(ROOT, "tests", "golden", key + ".ndsf.gz"))
+f = ndt_b200.FlatScene.load(key if os.path.exists(key) else os.path.join(ROOT, "tests", "golden", key + ".ndsf.gz"))
 if len(sys.argv) > 3:
     f = f.retarget(int(sys.argv[2]), int(sys.argv[3]))
 w, h = f.header.width, f.header.height
@@ -22,7 +22,7 @@ n = L.emu_stats_words()
 out = (C.c_ulonglong * n)()
 L.emu_stats_get(out)
 names = ["trace_kd", "aabb_hit", "nodes", "leaf_visits", "leaf_objs", "mb_skip", "bs_test", "bs_pass"] + \
-        ["prim%d" % i for i in range(16)] + ["prim_hit", "accept"]
+        ["prim%d" % i for i in range(16)] + ["prim_hit", "accept", "hc_child", "hc_bs_pass", "hc_hit"]
 d = dict(zip(names, list(out)))
 rays = st[0] + st[1] + st[2]
 print("frame %dx%d rays primary %d bounce %d shadow %d flops %d" % (w, h, st[0], st[1], st[2], st[5]))
