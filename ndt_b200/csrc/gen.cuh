@@ -484,6 +484,15 @@ struct WaveState : WaveHead {
     alignas(128) int nextB;
     alignas(128) int nextL;  /* ... of k_light / k_libm */
     alignas(128) int nextM;
+    alignas(128) int nextP0; /* ... of k_pre<0> / k_pre<1> */
+    alignas(128) int nextP1;
+    /* the walker lists k_pre hands to k_trace (WaveArgs::wl0 / wl1): warps whose 32 rays all walk claim 32 entries
+     * from the front (wfull, a multiple of 32: their bundle stays one 8x4 pixel block), the others append theirs
+     * from the back (wpart) */
+    alignas(128) int wfull0;
+    alignas(128) int wpart0;
+    alignas(128) int wfull1;
+    alignas(128) int wpart1;
     alignas(128) int nextR;  /* ... of k_resolve_dev / k_finish_dev */
     alignas(128) int nextF;
     alignas(128) int pool_overflow;  /* 1 record pool, 2 shadow queue, 3 more than WAVE_MAX_GEN generations */
@@ -525,6 +534,10 @@ struct WaveArgs {            /* constant for the life of a graph: pool pointers 
     uint32_t mb_stride, mb_words, mb_shift, pad2;
     const void *leafrec;
     const void *boxrec;
+    /* k_pre -> k_trace: the rays of the batch that walk the tree (index within the batch) and the interval of each
+     * inside the root box (tl, tu); [gen_cap] for the batch's own rays, [scap] for its shadow queries */
+    int *wl0, *wl1;
+    double2 *wt0, *wt1;
 };
 
 /* what k_begin gets by value */
@@ -554,8 +567,8 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, con
             if (active) primary_ray_at<NP>(sc, sxy[2 * (size_t)s], sxy[2 * (size_t)s + 1], o, v);
         } else {
             const int blk = s >> 5, bpr = hd->bpr;
-            tx = (blk % bpr) * 8 + (lane & 7);
-            ty = (blk / bpr) * 4 + (lane >> 3);
+            tx = (blk % bpr) * 8 + (s & 7);              /* slot s = pixel (s & 31) of block s >> 5, whichever lane asks */
+            ty = (blk / bpr) * 4 + ((s >> 3) & 3);
             active = active && tx < hd->tw && ty < hd->th;
             if (active) active = primary_ray<NP>(sc, hd->x0 + tx, hd->y0 + ty, o, v, hd->eye);
         }
@@ -565,7 +578,75 @@ __device__ __forceinline__ bool wave_ray(const Scene &sc, const WaveArgs &a, con
     return active;
 }
 
-/* MODE 0: the batch's own rays, MODE 1: its shadow queries */
+/* MODE 0: the batch's own rays, MODE 1: its shadow queries.
+ * k_pre: what every query does before it walks (warp.cuh: pre_walk) -- the infinite objects and the root box --
+ * for ALL rays of the batch, 12-32 warps per SM where k_trace has 8.  A ray that does not enter the root box gets
+ * its final answer here; a walker gets the state of the walk so far (the hit record holds trace()'s result over the
+ * infinite objects, wt its interval in the root box) and an entry in the walker list. */
+#ifndef NDT_PRE_MIN_BLOCKS
+#define NDT_PRE_MIN_BLOCKS 4
+#endif
+template <int NP, int MODE>
+__global__ void __launch_bounds__(BLOCK, NDT_PRE_MIN_BLOCKS) k_pre(const Scene sc, const WaveArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    WaveState *st = a.st;
+    const WaveHead *hd = wave_head_load(st);
+    const int gen = hd->gen, start = hd->start;
+    int count = hd->count;
+    if (MODE == 1) {             /* written by k_shade<A>, complete before this launch started */
+        count = *(volatile const int *)&st->stail;
+        if (count > a.scap) count = a.scap;
+    }
+    int *next = MODE ? &st->nextP1 : &st->nextP0;
+    int *wfull = MODE ? &st->wfull1 : &st->wfull0, *wpart = MODE ? &st->wpart1 : &st->wpart0;
+    int *wl = MODE ? a.wl1 : a.wl0;
+    double2 *wt = MODE ? a.wt1 : a.wt0;
+    const int lcap = MODE ? a.scap : a.gen_cap;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(next, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const int r = base + lane;
+        double o[NP], v[NP], limit = -1.0;
+        bool want;
+        int dir_light = -1, dest = 0;
+        if (MODE == 0) {
+            double frac; int depth, tx, ty;
+            want = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+        } else {
+            want = r < count;
+            if (want) {
+                int code;
+                ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)r, o, v, limit, code, dest);
+                dir_light = code - 1;
+            }
+        }
+        PreWalk pw;
+        pw.walking = false;
+        if (want) pre_walk<NP, true>(sc, o, v, limit, dir_light >= 0, pw);
+        const bool walk = want && pw.walking;
+        const unsigned wm = __ballot_sync(0xffffffffu, walk);
+        int pos = 0;
+        if (wm) {
+            const int nw = __popc(wm);
+            if (lane == 0) pos = nw == 32 ? atomicAdd(wfull, 32) : lcap - (atomicAdd(wpart, nw) + nw);
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(wm & ((1u << lane) - 1u));
+        }
+        if (want) {
+            /* a walker's record is what the walk starts from, everybody else's is final */
+            if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), pw.md, pw.id, pw.win, pw.ret);
+            else hit_store_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, pw.md, pw.id, pw.win, pw.ret);
+            if (walk) {
+                wl[pos] = r;
+                wt[pos] = make_double2(pw.tl, pw.tu);
+            }
+        }
+    }
+}
+
+/* k_trace: the walk, for the rays k_pre listed */
 template <int NP, int MODE, bool BIG>
 __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Scene sc, const WaveArgs a)
 {
@@ -578,7 +659,14 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
         count = *(volatile const int *)&st->stail;
         if (count > a.scap) count = a.scap;
     }
-    if ((int)(blockIdx.x * blockDim.x) >= count && blockIdx.x > 0) return;   /* the grid is sized for a full batch */
+    /* the walker list of k_pre, complete before this launch started */
+    const int n_full = *(volatile const int *)(MODE ? &st->wfull1 : &st->wfull0);
+    const int n_part = *(volatile const int *)(MODE ? &st->wpart1 : &st->wpart0);
+    const int n_walk = n_full + n_part;
+    const int lcap = MODE ? a.scap : a.gen_cap;
+    const int *wl = MODE ? a.wl1 : a.wl0;
+    const double2 *wt = MODE ? a.wt1 : a.wt0;
+    if ((int)(blockIdx.x * blockDim.x) >= n_walk && blockIdx.x > 0) return;   /* the grid is sized for a full batch */
     Mailbox mb;
     mb.bits = a.mb_bits; mb.stride = a.mb_stride;
     mb.slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -596,37 +684,42 @@ __global__ void __launch_bounds__(BLOCK, NDT_TRACE_MIN_BLOCKS) k_trace(const Sce
      * take thinner (16 ... 1 rays per draw) measured 6-17 % slower on every workload (one more trip to the counter
      * per draw, the same leaves staged by more warps): profiles/r02_experiments.md. */
     constexpr int draw = 32;
-    bool stop = false;
-    while (!stop) {
+    while (true) {
         /* (fetching the counter one batch ahead was measured slower: profiles/r01_experiments.md) */
         int base = 0;
         if (lane == 0) base = atomicAdd(next, draw);
         base = __shfl_sync(FULL, base, 0);
-        if (base >= count) break;
-        {
-            const int r = lane < draw ? base + lane : count;      /* lanes beyond the draw idle through the query */
-            double o[NP], v[NP], limit = -1.0;
-            bool want;
-            int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
-            int dest = 0;                /* MODE 1: index of the answer in shits[] */
+        if (base >= n_walk) break;
+        const int i = base + lane;
+        const bool want = i < n_walk;
+        const int pos = i < n_full ? i : lcap - n_part + (i - n_full);
+        double o[NP], v[NP], limit = -1.0;
+        int dir_light = -1;          /* >= 0: the any-hit query of that DIRECTIONAL light */
+        int dest = 0;                /* MODE 1: index of the answer in shits[] */
+        int r = 0;
+        PreWalk pw;
+        pw.md = -1; pw.tl = pw.tu = 0; pw.id = pw.win = -1; pw.ret = 0; pw.walking = want;
+        if (want) {
+            r = wl[pos];
+            const double2 tt = wt[pos];
+            pw.tl = tt.x; pw.tu = tt.y;
             if (MODE == 0) {
                 double frac; int depth, tx, ty;
-                want = wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+                wave_ray<NP>(sc, a, hd, gen, start, count, r, lane, o, v, frac, depth, tx, ty);
+                hit_load_s(a.hits, (size_t)a.cap, (size_t)(start + r), pw.md, pw.id, pw.win, pw.ret);
             } else {
-                want = r < count;
-                if (want) {
-                    int code;
-                    ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)r, o, v, limit, code, dest);
-                    dir_light = code - 1;
-                }
+                int code;
+                ray_load_s<NP>(a.srays, (size_t)a.scap, (size_t)r, o, v, limit, code, dest);
+                dir_light = code - 1;
+                hit_load_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, pw.md, pw.id, pw.win, pw.ret);
             }
-            Hit T;
-            trace_kd_warp<NP, BIG>(sc, ws, mb, want, o, v, limit, T, kd_overflow, dir_light);
-            if (ws.fault) { stop = true; break; }     /* warp-uniform (warp.cuh) */
-            if (want) {
-                if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), T.t, T.id, T.win, T.found);
-                else hit_store_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, T.t, T.id, T.win, T.found);
-            }
+        }
+        Hit T;
+        trace_kd_resume<NP, BIG>(sc, ws, mb, want, o, v, limit, pw, T, kd_overflow, dir_light);
+        if (ws.fault) break;         /* warp-uniform (warp.cuh) */
+        if (want) {
+            if (MODE == 0) hit_store_s(a.hits, (size_t)a.cap, (size_t)(start + r), T.t, T.id, T.win, T.found);
+            else hit_store_s(a.shits, (size_t)a.gen_cap * a.nl_eff, (size_t)dest, T.t, T.id, T.win, T.found);
         }
     }
     if (kd_overflow) atomicMax(&st->kd_fault, 1);
@@ -1027,6 +1120,9 @@ struct NpOps {
                        uint32_t *mb_bits, uint32_t mb_stride, uint32_t mb_words, uint32_t mb_shift, int *overflow,
                        const void *leafrec, const void *boxrec);
     /* for the graph nodes of the device-side generation loop (kernels.cu) */
+    const void *(*pre_fn)(int mode);
+    void (*pre)(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a);
+    int (*pre_grid)(int sm_count);
     const void *(*trace_fn)(int mode, int stage);   /* stage = Scene::any_boxed: bit 2 selects the big-leaf instantiation */
     const void *(*shade_fn)(int phase);
     size_t (*trace_smem_bytes)(int boxed);

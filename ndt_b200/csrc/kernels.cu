@@ -152,6 +152,7 @@ __global__ void k_begin(WaveState *st, const WaveBegin b, int gen_cap, unsigned 
     st->gen = 0; st->start = 0; st->count = b.n0 < gen_cap ? b.n0 : gen_cap;
     st->gen_start = 0; st->gen_count = b.n0;
     st->ngen = 0; st->iters = 0; st->cont = 1; st->resolve_g = 0; st->fail = 0;
+    st->nextP0 = 0; st->nextP1 = 0; st->wfull0 = 0; st->wpart0 = 0; st->wfull1 = 0; st->wpart1 = 0;
     st->tail = b.n0; st->next0 = 0; st->stail = 0; st->next1 = 0; st->nextA = 0; st->nextB = 0; st->nextR = 0; st->nextF = 0; st->nextL = 0; st->nextM = 0;
     st->pool_overflow = 0; st->kd_fault = 0;
     if (b.first) for (int k = 0; k < 8; ++k) stats[k] = 0ull;
@@ -192,6 +193,7 @@ __global__ void k_next_gen(WaveState *st, int cap, int gen_cap, cudaGraphConditi
         }
     }
     st->next0 = 0; st->stail = 0; st->next1 = 0; st->nextA = 0; st->nextB = 0; st->nextL = 0; st->nextM = 0;
+    st->nextP0 = 0; st->nextP1 = 0; st->wfull0 = 0; st->wpart0 = 0; st->wfull1 = 0; st->wpart1 = 0;
     st->cont = cont;
     if (!cont) st->fail = st->pool_overflow | (st->kd_fault << 8);
     if (use_h) cudaGraphSetConditional(h, cont ? 1u : 0u);
@@ -371,6 +373,8 @@ struct ndt_b200_ctx {
     int *d_aa_cnt; unsigned long long *d_aa_res;
     double *d_hgeo; size_t hgeo_bytes;   /* hit point + normal per ray of a batch */
     uint32_t *d_qmask; size_t qmask_bytes;
+    int *d_wl0, *d_wl1; size_t wl0_bytes, wl1_bytes;          /* walker lists of k_pre (gen.cuh) */
+    double2 *d_wt0, *d_wt1; size_t wt0_bytes, wt1_bytes;
     int trace_grid[8][8];                /* cached k_trace occupancy per (stage mode = Scene::any_boxed: 0, 1, 3; NP/2) */
     char *d_ana; size_t ana_bytes;       /* ANAGLYPH_3D: the two eyes' fp64 frames */
     int *d_ctr;                          /* fused path: [0] tail [1] next [2..3] overflow */
@@ -466,6 +470,7 @@ extern "C" void ndt_b200_destroy(ndt_b200_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_blob); cudaFree(c->d_leafrec); cudaFree(c->d_boxrec); cudaFree(c->d_nrec); cudaFree(c->d_nbox); cudaFree(c->d_rec); cudaFree(c->d_rays); cudaFree(c->d_mb);
     cudaFree(c->d_ana); cudaFree(c->d_hits); cudaFree(c->d_srays); cudaFree(c->d_shits); cudaFree(c->d_hgeo); cudaFree(c->d_qmask);
+    cudaFree(c->d_wl0); cudaFree(c->d_wl1); cudaFree(c->d_wt0); cudaFree(c->d_wt1);
     cudaFree(c->aa_img.p); cudaFree(c->aa_fin.p); cudaFree(c->aa_u8.p); cudaFree(c->aa_samp.p);
     cudaFree(c->aa_xy[0].p); cudaFree(c->aa_xy[1].p); cudaFree(c->d_aa_cnt); cudaFree(c->d_aa_res);
     for (int l = 0; l < 64; ++l) cudaFree(c->aa_cells[l].p);
@@ -544,14 +549,21 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     s.view = h->off_view ? (const double *)(b + h->off_view) : NULL;
     s.cam_type = h->cam_type; s.stereo_mode = h->stereo_mode; s.view_eyes = h->view_eyes;
     s.eye_override = 0; s.cam_dist = h->cam_dist;
+    {   /* k_pre inlines trace() over the infinite objects when they are all hplanes (the floor of every stock scene) */
+        const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
+        const int32_t *hinf = (const int32_t *)((const char *)fs + h->off_inf);
+        s.inf_hplanes = 1;
+        for (int i = 0; i < h->n_inf; ++i) if (ho[hinf[i]].type != NDT_T_HPLANE) s.inf_hplanes = 0;
+    }
     s.any_boxed = 0;
     {   /* k_pack_leaf gives orthotopes with a bounding sphere a box (warp.cuh: box_hit) */
         const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
         /* ... and, in boxed scenes, every other primitive the box of its bounding sphere.  Scenes without
          * orthotopes only pay for the second record stream when their leaves are large enough for the culls to
          * matter */
+        const bool force = getenv("NDT_B200_FORCE_BOXES") != NULL;      /* tests: the culls on scenes too small to need them */
         for (int i = 0; i < h->n_items && !s.any_boxed; ++i)
-            if (ho[i].bs_radius > 0 && (ho[i].type == NDT_T_ORTHOTOPE || h->max_leaf >= 48)) s.any_boxed = 1;
+            if (ho[i].bs_radius > 0 && (ho[i].type == NDT_T_ORTHOTOPE || h->max_leaf >= 48 || force)) s.any_boxed = 1;
         /* the slab test runs in fp32 with a fixed margin (warp.cuh: box_hit): only for scenes whose
          * coordinates keep its rounding error far below that margin */
         if (s.any_boxed) {
@@ -761,9 +773,12 @@ static int wave_graph_build(ndt_b200_ctx *c, int np, const WaveArgs &a, int n_sh
     WaveArgs wa = a;
     const size_t smem = ops->trace_smem_bytes(sc.any_boxed);
     void *targs[] = { &sc, &wa };
-    GK(add_kernel(b1, &n_prev, NULL, ops->trace_fn(0, sc.any_boxed), trace_grid, BLOCK, smem, targs));
+    const int pre_grid = ops->pre_grid(c->sm_count);
+    GK(add_kernel(b1, &n_prev, NULL, ops->pre_fn(0), pre_grid, BLOCK, 0, targs));
+    GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(0, sc.any_boxed), trace_grid, BLOCK, smem, targs)); n_prev = n_cur;
     GK(add_kernel(b1, &n_cur, &n_prev, ops->shade_fn(0), shade_grid, BLOCK, 0, targs)); n_prev = n_cur;
     if (n_sh > 0) {
+        GK(add_kernel(b1, &n_cur, &n_prev, ops->pre_fn(1), pre_grid, BLOCK, 0, targs)); n_prev = n_cur;
         GK(add_kernel(b1, &n_cur, &n_prev, ops->trace_fn(1, sc.any_boxed), trace_grid, BLOCK, smem, targs)); n_prev = n_cur;
         GK(add_kernel(b1, &n_cur, &n_prev, ops->light_fn(), light_grid(c), BLOCK, 0, targs)); n_prev = n_cur;
         int spec = c->hdr.specular, aux_word = np;
@@ -862,6 +877,10 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
         const uint32_t mw = (uint32_t)(h.n_lights + 1 + 31) / 32;
         if ((r = grow_pool(c, (void **)&c->d_hgeo, &c->hgeo_bytes, (size_t)gen_cap * 2 * np * sizeof(double)))) return r;
         if ((r = grow_pool(c, (void **)&c->d_qmask, &c->qmask_bytes, (size_t)gen_cap * mw * sizeof(uint32_t)))) return r;
+        if ((r = grow_pool(c, (void **)&c->d_wl0, &c->wl0_bytes, (size_t)gen_cap * sizeof(int)))) return r;
+        if ((r = grow_pool(c, (void **)&c->d_wl1, &c->wl1_bytes, scap * sizeof(int)))) return r;
+        if ((r = grow_pool(c, (void **)&c->d_wt0, &c->wt0_bytes, (size_t)gen_cap * sizeof(double2)))) return r;
+        if ((r = grow_pool(c, (void **)&c->d_wt1, &c->wt1_bytes, scap * sizeof(double2)))) return r;
 
         WaveArgs a;
         memset(&a, 0, sizeof a);
@@ -875,6 +894,7 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
         a.mb_words = mb_words; a.mb_shift = mb_shift;
         a.leafrec = c->d_leafrec;
         a.boxrec = c->d_boxrec;
+        a.wl0 = c->d_wl0; a.wl1 = c->d_wl1; a.wt0 = c->d_wt0; a.wt1 = c->d_wt1;
         const int shade_grid = ops->shade_grid(c->sm_count, gen_cap);
 
         WaveBegin wb;
@@ -918,9 +938,12 @@ static int launch_pass(ndt_b200_ctx *c, int x0, int y0, int tw, int th,
             int guard = 0;
             const bool trace_gens = getenv("NDT_B200_TRACE_GENS") != NULL;     /* the size of every generation, on stderr */
             do {
+                const int pre_grid = ops->pre_grid(c->sm_count);
+                ops->pre(0, pre_grid, st, c->sc, a);
                 ops->trace(0, full_grid, st, c->sc, a);
                 ops->shade(0, shade_grid, st, c->sc, a);
                 if (n_sh > 0) {
+                    ops->pre(1, pre_grid, st, c->sc, a);
                     ops->trace(1, full_grid, st, c->sc, a);
                     ops->light(light_grid(c), st, c->sc, a);
                     k_libm<<<libm_grid(c), 256, 0, st>>>(a, h.specular, np);
@@ -1037,8 +1060,8 @@ extern "C" int ndt_b200_sync(ndt_b200_ctx *c)
             if (hs->cont) return ndt_set_error(NDT_B200_E_CUDA, "the generation loop did not finish");
             c->last.rays_bounce += (uint64_t)(hs->tail - hs->n0);
             if ((uint32_t)hs->ngen > c->last.generations) c->last.generations = (uint32_t)hs->ngen;
-            /* k_begin, 4 or 7 kernels per batch, k_pre_resolve, 2 per folded generation, k_finish */
-            c->last.launches += 1 + (uint64_t)hs->iters * (c->n_sh_pending > 0 ? 7 : 4) + 1 +
+            /* k_begin, 5 or 9 kernels per batch, k_pre_resolve, 2 per folded generation, k_finish */
+            c->last.launches += 1 + (uint64_t)hs->iters * (c->n_sh_pending > 0 ? 9 : 5) + 1 +
                                 2 * (uint64_t)(hs->ngen > 1 ? hs->ngen - 1 : 0) + 1;
         }
         if (passes == 2) c->last.launches += 1;      /* k_anaglyph */

@@ -61,6 +61,19 @@ void shade(int phase, int blocks, cudaStream_t st, const Scene &sc, const WaveAr
     else k_shade<NP, 0><<<blocks, BLOCK, 0, st>>>(sc, a);
 }
 
+const void *pre_fn(int mode) { return mode ? (const void *)k_pre<NP, 1> : (const void *)k_pre<NP, 0>; }
+void pre(int mode, int blocks, cudaStream_t st, const Scene &sc, const WaveArgs &a)
+{
+    if (mode) k_pre<NP, 1><<<blocks, BLOCK, 0, st>>>(sc, a);
+    else k_pre<NP, 0><<<blocks, BLOCK, 0, st>>>(sc, a);
+}
+int pre_grid(int sm_count)
+{
+    int b0 = 0, b1 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_pre<NP, 0>, BLOCK, 0) != cudaSuccess || b0 < 1) b0 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_pre<NP, 1>, BLOCK, 0) != cudaSuccess || b1 < 1) b1 = 1;
+    return (b0 < b1 ? b0 : b1) * sm_count;
+}
 const void *trace_fn(int mode, int stage)
 {
     if (stage & 4) return mode ? (const void *)k_trace<NP, 1, true> : (const void *)k_trace<NP, 0, true>;
@@ -102,4 +115,4 @@ void trace_rays(int blocks, cudaStream_t st, const Scene &sc, int n_rays, const 
 }  // namespace
 
 extern const NpOps CAT(ndt_np_ops_, NDT_NP) = { trace_blocks_per_sm, trace, shade, blocks_per_sm, generation, pack_leaf, trace_rays,
-                                                     trace_fn, shade_fn, trace_smem, shade_grid, light_fn, light };
+                                                     pre_fn, pre, pre_grid, trace_fn, shade_fn, trace_smem, shade_grid, light_fn, light };

@@ -854,12 +854,84 @@ __device__ __forceinline__ double warp_leaf(const Scene &sc, WarpStage<NP> &ws, 
     return min_dist;
 }
 
-/* trace_kd (object.c:683) for the 32 rays of a warp.  Lanes with !want take
- * part in the staging only.  Same contract as core.cuh's trace_kd. */
+/* What every query does before it walks the tree: the infinite objects (kd-tree.c:592-594) and the root box
+ * (aabb_intersect, kd-tree.c:84-127).  Nine rays in ten of BASELINE config 2 and most of config 1's end here, so
+ * the wavefront runs this half in a kernel of its own at three times k_trace's occupancy (k_pre, gen.cuh) and
+ * hands k_trace the walkers only; md / id / win / ret / tl / tu are the state the walk picks up. */
+struct PreWalk {
+    double md;            /* trace()'s min_dist over the infinite objects (< 0: none) */
+    double tl, tu;        /* the ray's interval inside the root box, widened by EPS */
+    int id, win, ret;
+    bool walking;
+};
+/* SLIM: the form k_pre runs -- the root box straight from the ray's registers (unrolled) and, when every infinite
+ * object is an hplane (Scene::inf_hplanes), trace() specialised for that type and inlined; otherwise and in
+ * k_trace_rays / k_generation the rolled loops and the out-of-line list of round 1. */
+template <int NP, bool SLIM>
+__device__ __forceinline__ void pre_walk(const Scene &sc, const double *o, const double *v, double dist_limit, bool only_found,
+                                         PreWalk &p)
+{
+    p.walking = false;
+    p.tl = p.tu = 0;
+    if (SLIM && sc.inf_hplanes) {
+        Tally<false> none;
+        p.md = trace_list<NP, false, NDT_T_HPLANE>(sc, sc.inf, sc.n_inf, (Mailbox *)nullptr, o, v, dist_limit, p.id, p.win, none);
+    } else {
+        double ot[NP], vt[NP];
+        vcopy<NP>(ot, o);
+        vcopy<NP>(vt, v);
+        p.md = trace_list_slow_impl<NP>(sc, sc.inf, sc.n_inf, 0, ot, vt, dist_limit, &p.id, &p.win);
+    }
+    p.ret = !(p.md < 0);
+    if ((only_found && p.ret) || sc.n_nodes <= 0) return;
+    const double *lo = sc.aabb, *hi = sc.aabb + NP;
+    double l = -DBL_MAX, u = DBL_MAX;
+    bool behind = false;
+    if (SLIM) {
+        NDT_UNROLL
+        for (int i = 0; i < NP; ++i) {
+            if (i < sc.n && !behind) {
+                const double vi = v[i], oi = o[i];
+                if (!(fabs(vi) < EPS2)) {
+                    double a = (NDT_LDG(lo + i) - oi) / vi;
+                    double b = (NDT_LDG(hi + i) - oi) / vi;
+                    if (a > b) { double x = a; a = b; b = x; }
+                    if (a > l) l = a;
+                    if (b < u) u = b;
+                    if (u < -EPS) behind = true;
+                }
+            }
+        }
+    } else {
+        double o_dyn[NP], v_dyn[NP];
+        NDT_UNROLL
+        for (int i = 0; i < NP; ++i) { o_dyn[i] = o[i]; v_dyn[i] = v[i]; }
+        NDT_NO_UNROLL
+        for (int i = 0; i < sc.n && !behind; ++i) {
+            const double vi = v_dyn[i], oi = o_dyn[i];
+            if (!(fabs(vi) < EPS2)) {
+                double a = (NDT_LDG(lo + i) - oi) / vi;
+                double b = (NDT_LDG(hi + i) - oi) / vi;
+                if (a > b) { double x = a; a = b; b = x; }
+                if (a > l) l = a;
+                if (b < u) u = b;
+                if (u < -EPS) behind = true;
+            }
+        }
+    }
+    if (behind) return;
+    l -= EPS;
+    u += EPS;
+    p.tl = l; p.tu = u;
+    p.walking = (u >= -EPS) && (l <= u);
+}
+
+/* trace_kd (object.c:683) for the 32 rays of a warp, from where pre_walk left off: lanes with `walking` walk
+ * the tree, the others take part in the staging only.  Same contract as core.cuh's trace_kd. */
 template <int NP, bool BIG>
-__device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool want,
-                                              const double *o, const double *v, double dist_limit,
-                                              Hit &out, int &overflow, int dir_light)
+__device__ __forceinline__ void trace_kd_resume(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool walking,
+                                                const double *o, const double *v, double dist_limit, const PreWalk &pw,
+                                                Hit &out, int &overflow, int dir_light)
 {
     /* dir_light >= 0: the any-hit query of DIRECTIONAL light dir_light (ndt.c:241-249): the caller consumes
      * nothing but the return value */
@@ -872,58 +944,28 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
      * this per-ray prologue runs once per query and only costs instruction fetches) */
     double o_dyn[NP], v_dyn[NP], vinv[NP];
     float obox[NP], vbox[NP];       /* the ray in fp32 for the box cull (local memory; registers only inside the broad loop) */
-    double t = DBL_MAX, md = -1;
-    int ret = 0;
-    out.id = -1;
-    out.win = -1;
-    bool walking = false;
-    double tl = 0, tu = 0;
-    if (want) {
+    double t = DBL_MAX, md = pw.md;
+    int ret = pw.ret;
+    out.id = pw.id;
+    out.win = pw.win;
+    double tl = pw.tl, tu = pw.tu;
+    if (md > EPS) t = md;
+    if (walking) {
         NDT_UNROLL
         for (int i = 0; i < NP; ++i) { o_dyn[i] = o[i]; v_dyn[i] = v[i]; }
-        /* infinite objects first, linear, no mailbox (kd-tree.c:592-594) */
-        md = trace_list_slow_impl<NP>(sc, sc.inf, sc.n_inf, 0, o_dyn, v_dyn, dist_limit, &out.id, &out.win);
-        ret = !(md < 0);
-        if (md > EPS) t = md;
-        if (!(only_found && ret) && sc.n_nodes > 0) {
-            /* aabb_intersect, kd-tree.c:84-127 (aabb_hit of core.cuh, rolled) */
-            const double *lo = sc.aabb, *hi = sc.aabb + NP;
-            double l = -DBL_MAX, u = DBL_MAX;
-            bool behind = false;
-            NDT_NO_UNROLL
-            for (int i = 0; i < sc.n && !behind; ++i) {
-                const double vi = v_dyn[i], oi = o_dyn[i];
-                if (!(fabs(vi) < EPS2)) {
-                    double a = (NDT_LDG(lo + i) - oi) / vi;
-                    double b = (NDT_LDG(hi + i) - oi) / vi;
-                    if (a > b) { double x = a; a = b; b = x; }
-                    if (a > l) l = a;
-                    if (b < u) u = b;
-                    if (u < -EPS) behind = true;
-                }
-            }
-            if (!behind) {
-                l -= EPS;
-                u += EPS;
-                tl = l; tu = u;
-                if ((u >= -EPS) && (l <= u)) {
-                    mb.clear();
-                    walking = true;
-                    /* only the rays that enter the root box (12 % in config 2) need the per-axis
-                     * reciprocals of the walk and of the box cull */
-                    NDT_NO_UNROLL
-                    for (int i = 0; i < NP; ++i) {
-                        double vi = v_dyn[i], r;
-                        if (vi < EPS2 && vi >= 0.0) r = INV_EPS2;
-                        else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
-                        else r = 1.0 / vi;
-                        vinv[i] = r;
-                        if (sc.any_boxed) {     /* the slab test wants the true reciprocal (+-inf for a zero component) */
-                            obox[i] = (float)o_dyn[i];
-                            vbox[i] = (float)(1.0 / vi);
-                        }
-                    }
-                }
+        mb.clear();
+        /* only the rays that enter the root box (12 % in config 2) need the per-axis
+         * reciprocals of the walk and of the box cull */
+        NDT_NO_UNROLL
+        for (int i = 0; i < NP; ++i) {
+            double vi = v_dyn[i], r;
+            if (vi < EPS2 && vi >= 0.0) r = INV_EPS2;
+            else if (vi > -EPS2 && vi <= 0.0) r = -INV_EPS2;
+            else r = 1.0 / vi;
+            vinv[i] = r;
+            if (sc.any_boxed) {     /* the slab test wants the true reciprocal (+-inf for a zero component) */
+                obox[i] = (float)o_dyn[i];
+                vbox[i] = (float)(1.0 / vi);
             }
         }
     }
@@ -1042,6 +1084,18 @@ __device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws
     }
     out.found = ret;
     out.t = md;
+}
+
+/* the whole query (k_trace_rays, k_generation): lanes with !want take part in the staging only */
+template <int NP, bool BIG>
+__device__ __forceinline__ void trace_kd_warp(const Scene &sc, WarpStage<NP> &ws, Mailbox &mb, bool want,
+                                              const double *o, const double *v, double dist_limit,
+                                              Hit &out, int &overflow, int dir_light)
+{
+    PreWalk pw;
+    pw.md = -1; pw.tl = pw.tu = 0; pw.id = pw.win = -1; pw.ret = 0; pw.walking = false;
+    if (want) pre_walk<NP, false>(sc, o, v, dist_limit, dir_light >= 0, pw);
+    trace_kd_resume<NP, BIG>(sc, ws, mb, pw.walking, o, v, dist_limit, pw, out, overflow, dir_light);
 }
 
 /* process_ray (wave.cuh) for a warp: every lane runs the same sequence of

@@ -97,3 +97,91 @@ def test_random_scene_with_a_bounded_tree_against_brute_force(ref, N_OBJECTS, gr
     got_id = np.array([frame.obj_id[j, i] for j, i in pix])
     assert np.array_equal(got_id, oid[:n_prim])
     assert n_hits > min(500, n_extra // 2)
+
+
+def test_staged_face_lists_equal_the_scalar_face_loop(ref, monkeypatch):
+    """The face list nested in an hcube (472 orthotopes for a 6-cube) goes through the warp's second staging area
+    (warp.cuh: warp_nested -- box / bundle culls, staged narrow phase) when many lanes ask for the cube, and
+    across the lanes for one ray at a time when few do (hcube_one_ray); NDT_B200_NO_NESTED_STAGE=1 at upload
+    keeps round 1's scalar loop (core.cuh: trace_list).  Same answers bit for bit on coherent bundles aimed at
+    the cubes, on incoherent rays from inside the cloud, and on a frame."""
+    n_obj = 400
+    ref.open_scene("random")
+    ref.begin_frame_nokd(6, 0, 300, str(n_obj))
+    try:
+        rc = ndt_b200.kd_tree_build_bounded(ref.kdtree_ptr, ref.items_ptr, max_depth=14, leaf_size=48, max_growth=1.5)
+        assert rc in (0, 1)
+        flat = ndt_b200.flatten(ref.scene_ptr, ref.kdtree_ptr, W, H, 128, 1, ref.get_bounds_ptr)
+    finally:
+        ref.end_frame()
+    hd = flat.header
+    obj_type = np.frombuffer(flat.blob, np.int32, hd.n_objects * 24, hd.off_objects).reshape(hd.n_objects, 24)[:, 0]
+    cubes = np.flatnonzero(obj_type[:hd.n_items] == 4)
+    assert len(cubes) > 10 and hd.n_objects > hd.n_items
+    bs = np.frombuffer(flat.blob, np.float64, hd.n_objects * (hd.npad + 2), hd.off_bspheres).reshape(hd.n_objects, hd.npad + 2)
+    rng = np.random.default_rng(11)
+    o, v = [], []
+    for k in range(60):                     # bundles of 32 nearly parallel rays through a cube: every lane asks for it
+        c = bs[cubes[k % len(cubes)], :hd.n]
+        src = rng.uniform(-20.0, 30.0, size=hd.n)
+        for _ in range(32):
+            d = c + rng.normal(size=hd.n) * 0.05 - src
+            o.append(src.copy()); v.append(d / np.sqrt((d * d).sum()))
+    for k in range(3000):                   # incoherent: from inside the cloud at an object
+        i = rng.integers(hd.n_items)
+        src = rng.uniform(2.0, 12.0, size=hd.n)
+        d = bs[i, :hd.n] + rng.normal(size=hd.n) * abs(bs[i, hd.npad]) * 0.4 - src
+        o.append(src); v.append(d / np.sqrt((d * d).sum()))
+    o = np.array(o); v = np.array(v)
+    a = ndt_b200.Context(0)
+    b = ndt_b200.Context(0)
+    try:
+        a.upload(flat)
+        monkeypatch.setenv("NDT_B200_NO_NESTED_STAGE", "1")
+        b.upload(flat)
+        monkeypatch.delenv("NDT_B200_NO_NESTED_STAGE")
+        ra = a.trace_rays(o, v)
+        rb = b.trace_rays(o, v)
+        fa = a.render_tile(0, 0, W, H)
+        fb = b.render_tile(0, 0, W, H)
+    finally:
+        a.close(); b.close()
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    # (random.c's cubes have random, non-orthogonal edge directions: with orthotope.c's per-axis projections their
+    # faces all but never report a hit -- the face lists are walked, nothing is accepted; the cube of
+    # scenes/hypercube.c below is hit)
+    assert int((ra[1] >= 0).sum()) > 1000
+    assert np.array_equal(fa.obj_id, fb.obj_id)
+    assert np.array_equal(fa.rgba_f64.view(np.uint8), fb.rgba_f64.view(np.uint8))
+
+
+@pytest.mark.parametrize("key,w,h", [("hypercube5d_hcube", 640, 360), ("view_vr5d", 96, 54)])
+def test_staged_face_lists_on_a_cube_that_is_hit(key, w, h, monkeypatch):
+    """scenes/hypercube.c -u hcube: one 5-cube (130 faces of 2, 3 and 4 dimensions) in front of the camera.  The scene is too small for the box culls
+    to be switched on; NDT_B200_FORCE_BOXES=1 at upload switches them on, and with them the staged face lists.
+    The frame must not change (the plain render is checked against the oracle in test_gpu_parity.py)."""
+    from conftest import load_flat
+    flat = load_flat(key)
+    if (w, h) != (flat.header.width, flat.header.height):
+        flat = flat.retarget(w, h)
+    a = ndt_b200.Context(0)
+    b = ndt_b200.Context(0)
+    try:
+        a.upload(flat)
+        monkeypatch.setenv("NDT_B200_FORCE_BOXES", "1")
+        b.upload(flat)
+        monkeypatch.delenv("NDT_B200_FORCE_BOXES")
+        fa = a.render_tile(0, 0, w, h)
+        fb = b.render_tile(0, 0, w, h)
+    finally:
+        a.close(); b.close()
+    hd = flat.header
+    obj_type = np.frombuffer(flat.blob, np.int32, hd.n_objects * 24, hd.off_objects).reshape(hd.n_objects, 24)[:, 0]
+    cubes = np.flatnonzero(obj_type[:hd.n_items] == 4)
+    bs = np.frombuffer(flat.blob, np.float64, hd.n_objects * (hd.npad + 2), hd.off_bspheres).reshape(hd.n_objects, hd.npad + 2)
+    assert len(cubes) >= 1 and bs[cubes[0], hd.npad] > 0          # a bounding sphere: the cube gets a box, the scene the culls
+    assert int(np.isin(fa.obj_id, cubes).sum()) >= 16
+    assert np.array_equal(fa.hit, fb.hit) and np.array_equal(fa.obj_id, fb.obj_id)
+    assert np.array_equal(fa.rgba_f64.view(np.uint8), fb.rgba_f64.view(np.uint8))
+    assert fb.stats.launches != 0 and fa.stats.rays_unique == fb.stats.rays_unique

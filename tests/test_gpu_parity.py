@@ -254,29 +254,6 @@ def test_graph_and_host_loop_agree(monkeypatch):
         a.close(); b.close()
 
 
-def test_staged_face_lists_equal_the_scalar_face_loop(monkeypatch):
-    """The face list nested in an hcube goes through the warp's second staging area (warp_nested: box / bundle culls,
-    staged narrow phase) or, for a ray at a time, across the lanes (hcube_one_ray); NDT_B200_NO_NESTED_STAGE=1 at
-    upload keeps the scalar loop of round 1 (core.cuh: trace_list).  Same frame bit for bit, at a size where a
-    bundle is tight (gen 0) and the bounce generations are incoherent."""
-    flat = load_flat("config3_random6d").retarget(640, 360)
-    w, h = flat.header.width, flat.header.height
-    a = ndt_b200.Context(0)
-    b = ndt_b200.Context(0)
-    try:
-        a.upload(flat)
-        monkeypatch.setenv("NDT_B200_NO_NESTED_STAGE", "1")
-        b.upload(flat)
-        monkeypatch.delenv("NDT_B200_NO_NESTED_STAGE")
-        fa = a.render_tile(0, 0, w, h)
-        fb = b.render_tile(0, 0, w, h)
-        assert np.array_equal(fa.hit, fb.hit) and np.array_equal(fa.obj_id, fb.obj_id)
-        assert bits_equal(fa.rgba_f64, fb.rgba_f64)
-        assert fa.stats.rays_unique == fb.stats.rays_unique and fa.hit.sum() > 100
-    finally:
-        a.close(); b.close()
-
-
 # BASELINE.json configs at the sizes bench.py times them at (VERDICT r1, missing #1): the culls of k_trace depend on
 # how tight an 8x4-pixel bundle is, i.e. on the resolution, so parity at 96x54 says nothing about 1920x1080.
 FULL_SIZE = [("config2_hypercube8d", 1920, 1080), ("config4_balls5d", 3840, 2160), ("config5_yaml10d", 1920, 1080)]
