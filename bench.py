@@ -75,7 +75,7 @@ WORKLOADS = {
 }
 FRAMES_PER_GPU = 4
 ANIM_FRAMES = 32
-IN_FLIGHT = int(os.environ.get("NDT_IN_FLIGHT", "2"))   # frames in flight per GPU: one ndt_b200 context (own CUDA stream) and one host thread each
+IN_FLIGHT = int(os.environ.get("NDT_IN_FLIGHT", "4"))   # frames in flight per GPU: one ndt_b200 context (own CUDA stream) and one host thread each; 4 = the whole step: the latency-bound late generations of one frame (config 1: ten generations of < 20 000 rays, 0.19 ms each) run under the bulk of the others (2 in flight: config 1 -7 %, config 2 -1 %)
 SAMPLE_DIV = 4          # reference sample: width/4 x height/4 = 1/16 of the pixels
 
 
@@ -592,7 +592,7 @@ def build_roofline(workload, solo_ms, flops_frame, peak_nf, peak_f, step_s):
     if prof and solo_ms > 0 and peak:
         ops = prof["fp64_thread_inst_dadd_dmul_dfma"]
         kt = prof["kernels"]
-        tr = [v for k, v in kt.items() if "k_trace" in k]
+        tr = [v for k, v in kt.items() if "k_trace" in k or "k_pre<" in k]       # the query: k_pre (before the walk) + k_trace (the walk)
         tr_ops = sum(v["dadd"] + v["dmul"] + v["dfma"] for v in tr)
         tr_share = sum(v["ms_under_ncu"] for v in tr) / prof["frame_kernel_ms_under_ncu"]
         achieved = ops / (solo_ms * 1e-3) / 1e12
@@ -601,13 +601,14 @@ def build_roofline(workload, solo_ms, flops_frame, peak_nf, peak_f, step_s):
             "executed_fp64_thread_inst_per_frame": ops,
             "executed_source": os.path.relpath(p, ROOT) + ": smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum over "
                                "the kernels of one frame (ncu, this build); DFMA (division / sqrt / libm sequences) counted as ONE",
-            "kernel": "k_trace<NP,0> + k_trace<NP,1> (nearest-hit and shadow queries)",
+            "kernel": "the nearest-hit and shadow queries: k_pre<NP,0|1> (infinite objects + root box, every ray) + k_trace<NP,0|1> (the walk, "
+                      "the rays that enter the root box)",
             "kernel_share_of_frame": tr_share,
             "kernel_achieved": tr_ops / (solo_ms * 1e-3 * tr_share) / 1e12 if tr_share > 0 else None,
             "kernel_frac": tr_ops / (solo_ms * 1e-3 * tr_share) / 1e12 / peak if tr_share > 0 else None,
             "kernel_fp64_pipe_active_pct_ncu": [v["fp64_pipe_active_pct"] for v in tr],
             "traffic": prof.get("dram_bytes_k_trace"),
-            "traffic_unit": "bytes, dram__bytes_read.sum + dram__bytes_write.sum of the k_trace launches of one frame (same ncu pass); "
+            "traffic_unit": "bytes, dram__bytes_read.sum + dram__bytes_write.sum of the k_pre + k_trace launches of one frame (same ncu pass); "
                             "the scene is L2-resident, the traffic is ray queues and hit records",
         })
     else:

@@ -66,7 +66,7 @@ def main():
                               "dram_bytes": a["dram"]}
     allops = sum(k["dadd"] + k["dmul"] + k["dfma"] for k in res["kernels"].values())
     res["fp64_thread_inst_dadd_dmul_dfma"] = allops
-    res["dram_bytes_k_trace"] = sum(k["dram_bytes"] for n_, k in res["kernels"].items() if "k_trace" in n_) or None
+    res["dram_bytes_k_trace"] = sum(k["dram_bytes"] for n_, k in res["kernels"].items() if "k_trace" in n_ or "k_pre<" in n_) or None
     res["source"] = "ncu --metrics gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum,... " \
                     "--clock-control none on `NDT_B200_NO_GRAPH=1 python tools/perf_frame.py <workload> 1` (second frame); " + path
     print(f"{'frame':28s} {'':4s} {tot_ms:8.3f} {'':6s} {allops/1e9:32.3f}")
