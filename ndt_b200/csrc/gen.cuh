@@ -598,16 +598,13 @@ __global__ void __launch_bounds__(BLOCK, NDT_PRE_MIN_BLOCKS) k_pre(const Scene s
         count = *(volatile const int *)&st->stail;
         if (count > a.scap) count = a.scap;
     }
-    int *next = MODE ? &st->nextP1 : &st->nextP0;
     int *wfull = MODE ? &st->wfull1 : &st->wfull0, *wpart = MODE ? &st->wpart1 : &st->wpart0;
     int *wl = MODE ? a.wl1 : a.wl0;
     double2 *wt = MODE ? a.wt1 : a.wt0;
     const int lcap = MODE ? a.scap : a.gen_cap;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(next, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
+    /* a static stride: what a ray costs here hardly varies (k_trace draws from a counter: there it varies a lot) */
+    const int stride = (int)(gridDim.x * blockDim.x);
+    for (int base = (int)(blockIdx.x * blockDim.x) + (threadIdx.x & ~31); base < count; base += stride) {
         const int r = base + lane;
         double o[NP], v[NP], limit = -1.0;
         bool want;

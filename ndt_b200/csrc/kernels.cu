@@ -549,11 +549,16 @@ extern "C" int ndt_b200_upload(ndt_b200_ctx *c, const ndt_flat_scene *fs)
     s.view = h->off_view ? (const double *)(b + h->off_view) : NULL;
     s.cam_type = h->cam_type; s.stereo_mode = h->stereo_mode; s.view_eyes = h->view_eyes;
     s.eye_override = 0; s.cam_dist = h->cam_dist;
-    {   /* k_pre inlines trace() over the infinite objects when they are all hplanes (the floor of every stock scene) */
+    {   /* k_pre inlines trace() over the infinite objects when they are hplanes / cylinders / hcylinders (what the stock plugins make infinite) */
         const ndt_flat_object *ho = (const ndt_flat_object *)((const char *)fs + h->off_objects);
         const int32_t *hinf = (const int32_t *)((const char *)fs + h->off_inf);
         s.inf_hplanes = 1;
-        for (int i = 0; i < h->n_inf; ++i) if (ho[hinf[i]].type != NDT_T_HPLANE) s.inf_hplanes = 0;
+        for (int i = 0; i < h->n_inf; ++i) {
+            const int t = ho[hinf[i]].type;
+            if (t == NDT_T_HPLANE) continue;
+            if (t == NDT_T_CYLINDER || t == NDT_T_HCYLINDER) { if (s.inf_hplanes) s.inf_hplanes = 2; }
+            else s.inf_hplanes = 0;
+        }
     }
     s.any_boxed = 0;
     {   /* k_pack_leaf gives orthotopes with a bounding sphere a box (warp.cuh: box_hit) */

@@ -865,7 +865,8 @@ struct PreWalk {
     bool walking;
 };
 /* SLIM: the form k_pre runs -- the root box straight from the ray's registers (unrolled) and, when every infinite
- * object is an hplane (Scene::inf_hplanes), trace() specialised for that type and inlined; otherwise and in
+ * object is an hplane, a cylinder or an hcylinder (Scene::inf_hplanes), trace() specialised for those types and inlined;
+ * otherwise and in
  * k_trace_rays / k_generation the rolled loops and the out-of-line list of round 1. */
 template <int NP, bool SLIM>
 __device__ __forceinline__ void pre_walk(const Scene &sc, const double *o, const double *v, double dist_limit, bool only_found,
@@ -873,9 +874,13 @@ __device__ __forceinline__ void pre_walk(const Scene &sc, const double *o, const
 {
     p.walking = false;
     p.tl = p.tu = 0;
-    if (SLIM && sc.inf_hplanes) {
+    if (SLIM && sc.inf_hplanes == 1) {
         Tally<false> none;
-        p.md = trace_list<NP, false, NDT_T_HPLANE>(sc, sc.inf, sc.n_inf, (Mailbox *)nullptr, o, v, dist_limit, p.id, p.win, none);
+        p.md = trace_list<NP, false, 1u << NDT_T_HPLANE>(sc, sc.inf, sc.n_inf, (Mailbox *)nullptr, o, v, dist_limit, p.id, p.win, none);
+    } else if (SLIM && sc.inf_hplanes == 2) {
+        constexpr unsigned INF_TYPES = (1u << NDT_T_HPLANE) | (1u << NDT_T_CYLINDER) | (1u << NDT_T_HCYLINDER);
+        Tally<false> none;
+        p.md = trace_list<NP, false, INF_TYPES>(sc, sc.inf, sc.n_inf, (Mailbox *)nullptr, o, v, dist_limit, p.id, p.win, none);
     } else {
         double ot[NP], vt[NP];
         vcopy<NP>(ot, o);
