@@ -233,6 +233,10 @@ def plugin_e2e(workload):
     ref = os.path.join(ROOT, "oracle", "_ref")
     if not os.path.exists(demo) or not os.path.exists(os.path.join(ref, "libndt_ref.so")):
         return {"unavailable": "integration/ndt_b200_demo not built (needs oracle/_ref)"}
+    if workload == "config5_yaml":
+        # the YAML file holds ONE document = one frame (scene.c:2067-2088); asked for frames 1..4 the reference's loader
+        # never returns, and this measurement is a five-frame loop
+        return {"unavailable": "one-document YAML scene: the five-frame loop of this measurement does not apply"}
     import tempfile
     base = [demo, "-d", str(dims), "-r", f"{W}x{H}", "-o", os.path.join(ref, "objects")]
     if workload == "config4_anim":
@@ -250,7 +254,7 @@ def plugin_e2e(workload):
             # start-up and the graph build, so the per-frame time is taken over frames 2..5
             t0 = time.perf_counter()
             r = subprocess.run(base + ["-f", f"{frame}:{frame + 4}:300"], cwd=tmp, capture_output=True, text=True,
-                               timeout=900, env=dict(os.environ, NDT_B200_TIMING="1", NDT_B200_KD_TIMING="1"))
+                               stdin=subprocess.DEVNULL, timeout=240, env=dict(os.environ, NDT_B200_TIMING="1", NDT_B200_KD_TIMING="1"))
             wall = time.perf_counter() - t0
             if r.returncode != 0:
                 return {"unavailable": (r.stdout[-300:] + r.stderr[-300:]).replace("\n", " ")}
