@@ -1,6 +1,6 @@
 /*
- * gen.cuh -- the kernels that depend on the padded dimension NP (k_pack_leaf,
- * k_generation, k_trace_rays) and the per-NP launch table.  Each NP is
+ * gen.cuh -- the kernels that depend on the padded dimension NP (k_pack_leaf, the wavefront's k_pre / k_trace /
+ * k_shade / k_light, the fused k_generation, the probe k_trace_rays) and the per-NP launch table.  Each NP is
  * instantiated in its own translation unit (np_inst.cu built with -DNDT_NP=N)
  * so the five dimensions compile in parallel; kernels.cu looks the launchers up
  * through ndt_np_ops().

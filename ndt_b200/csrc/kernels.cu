@@ -4,9 +4,12 @@
  * One render = one pass over the tile's rays, generation by generation, with the loop ON THE DEVICE:
  *   k_begin            resets WaveState (gen.cuh): generation 0 = the tile's pixels (8x4 blocks per warp)
  *   WHILE (CUDA graph conditional node; condition set by k_next_gen)
- *     k_trace<NP,0>    nearest hit of every ray of the batch            -> HitRec
+ *     k_pre<NP,0>      every ray of the batch: the infinite objects and the root box; rays that do not
+ *                      enter it are answered, the others listed                       -> HitRec, walker list
+ *     k_trace<NP,0>    the listed rays walk the kd-tree: nearest hit                  -> HitRec
  *     k_shade<NP,A>    hit point, normal, side tests; one shadow query per light that needs one
- *     k_trace<NP,1>    the shadow queries                                -> HitRec per (ray, light)
+ *     k_pre<NP,1>, k_trace<NP,1>   the same for the shadow queries                    -> HitRec per (ray, light)
+ *     k_light<NP>, k_libm          per query: the vector half of the lit term, then acos / cos / pow
  *     k_shade<NP,B>    the light loop in the reference's order, RayRec, reflection / refraction rays
  *                      appended to the next generation (two ballots + one atomic per warp)
  *     k_next_gen       next batch / next generation / stop
