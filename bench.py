@@ -12,7 +12,7 @@ the flat blob the struct-ABI adapter produced from the reference's own scene + k
 (tests/golden/, made by tests/golden/make_golden.py), so nothing under oracle/ runs on our arm.
 
 A STEP renders FRAMES_PER_GPU frames per GPU ("weak": per-GPU work is fixed as N grows).  Each
-rank renders its own frames with IN_FLIGHT contexts (two frames in flight per GPU, pulled from a
+rank renders its own frames with IN_FLIGHT contexts (four frames in flight per GPU, pulled from a
 rank-local queue); the only exchange is "finished frames -> rank 0":
 
   value  device-resident: scene already in HBM, every frame ends up in rank 0's HBM.  N>1: each
