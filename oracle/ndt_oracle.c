@@ -5,7 +5,7 @@
  * leg may load it.
  *
  * Parity status: PINNED.  The reference ships no golden vectors (SURVEY.md
- * section 4), so the pin is the reference itself: tests/test_oracle_vs_ref.py
+ * section 4), so the pin is the reference itself: tests/test_oracle.py
  * runs the unmodified reference (oracle/_ref, built from /root/reference by
  * oracle/Makefile) and this file on the same scenes and requires bit-identical
  * fp64 framebuffers and hit/id buffers; tests/golden/ holds the digests of
